@@ -1,0 +1,211 @@
+"""ctypes binding of libbgp_b200.so (C ABI declared in include/branchedgp_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or no sm_100 GPU is visible, creating an
+``Engine`` raises.  numpy is the only Python dependency of this module; torch is never imported here.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+KERNEL_MATERN32 = 0
+KERNEL_SQEXP = 1
+MODEL_BGP = 0
+MODEL_MBGP = 1
+
+_LIB_NAME = "libbgp_b200.so"
+_lib = None
+_lib_lock = threading.Lock()
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/branchedgp_b200.h declares (tests check this).
+SIGNATURES = {
+    "bgp_version": (ctypes.c_int, []),
+    "bgp_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bgp_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "bgp_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "bgp_device_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "bgp_set_max_slots": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bgp_dense_slot_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "bgp_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
+    "bgp_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "bgp_dense_elbo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_dense_elbo_grad_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_get_phi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_debug_set_stop_phase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bgp_debug_padded_size": (ctypes.c_int, [ctypes.c_int]),
+    "bgp_debug_dense_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "bgp_debug_dense_vector": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+}
+
+
+class BgpError(RuntimeError):
+    """The CUDA library reported an error (or is not available)."""
+
+
+class CholeskyError(BgpError):
+    """Non-positive pivot in a Cholesky factorisation (the reference's tf.linalg.cholesky InvalidArgumentError)."""
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library():
+    """dlopen the in-tree shared library and declare the signatures.  Raises BgpError when it is missing."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            raise BgpError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C branchedgp_b200/csrc); there is no CPU fallback")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """One handle on one GPU.  Not thread-safe; create one per host thread."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.bgp_create(int(device), ctypes.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self._lib.bgp_last_error(h).decode() if h else "bgp_create failed"
+            raise BgpError(f"bgp_create(device={device}) failed: {msg}")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bgp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc, what):
+        if rc != 0:
+            raise BgpError(f"{what} failed (code {rc}): {self._lib.bgp_last_error(self._h).decode()}")
+
+    @property
+    def sm_count(self):
+        return self._lib.bgp_device_sm_count(self._h)
+
+    def set_max_slots(self, n):
+        self._check(self._lib.bgp_set_max_slots(self._h, int(n)), "bgp_set_max_slots")
+
+    # ------------------------------------------------------------------ dense bound
+    def dense_elbo_grad(self, t, Y, item_gene, b, prior, hyp, logPhi, kernel=KERNEL_MATERN32, model=MODEL_BGP,
+                        kl_weight=1.0, KConst=None, want_grad=True, check=True):
+        """Host-array entry: Y [nY,N,D], item_gene [count], b [count], hyp [count,3], logPhi [count,N,3N]."""
+        t = _f64(t)
+        Y = _f64(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        nY, N, D = Y.shape
+        item_gene = np.ascontiguousarray(item_gene, dtype=np.int32)
+        count = item_gene.size
+        b = _f64(b).reshape(count)
+        hyp = _f64(hyp).reshape(count, 3)
+        prior = _f64(prior)
+        logPhi = _f64(logPhi).reshape(count, N, 3 * N)
+        assert t.shape == (N,)
+        assert prior.shape == (N, 3 if model == MODEL_MBGP else 2)
+        assert item_gene.min() >= 0 and item_gene.max() < nY
+        if KConst is not None:
+            KConst = _f64(KConst)
+            assert KConst.shape == (3 * N, 3 * N)
+        elbo = np.empty(count)
+        status = np.empty(count, dtype=np.int32)
+        grad_hyp = np.zeros((count, 4)) if want_grad else None
+        grad_logPhi = np.empty((count, N, 3 * N)) if want_grad else None
+        rc = self._lib.bgp_dense_elbo_grad_host(self._h, count, N, D, _ptr(t), _ptr(Y), nY, _ptr(item_gene), _ptr(b),
+                                                _ptr(prior), _ptr(hyp), int(kernel), int(model), float(kl_weight),
+                                                _ptr(logPhi), _ptr(KConst), int(bool(want_grad)), _ptr(elbo),
+                                                _ptr(grad_hyp), _ptr(grad_logPhi), _ptr(status))
+        self._check(rc, "bgp_dense_elbo_grad_host")
+        if check and (status != 0).any():
+            i = int(np.flatnonzero(status)[0])
+            raise CholeskyError(f"Cholesky decomposition was not successful for work item {i} (status {int(status[i])}): "
+                                "the input might not be valid")
+        return dict(elbo=elbo, grad_hyp=grad_hyp, grad_logPhi=grad_logPhi, status=status)
+
+    def dense_elbo_grad_device(self, count, N, D, t, Y, nY, item_gene, b, prior, hyp, logPhi, elbo, grad_hyp, grad_logPhi,
+                               status, kernel=KERNEL_MATERN32, model=MODEL_BGP, kl_weight=1.0, KConst=0, want_grad=True,
+                               stream=0):
+        """Device-pointer entry (integers from e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+        rc = self._lib.bgp_dense_elbo_grad(self._h, count, N, D, t, Y, nY, item_gene, b, prior, hyp, int(kernel), int(model),
+                                           float(kl_weight), logPhi, KConst or None, int(bool(want_grad)), elbo,
+                                           grad_hyp or None, grad_logPhi or None, status, stream or None)
+        self._check(rc, "bgp_dense_elbo_grad")
+
+    def get_phi(self, logPhi):
+        logPhi = _f64(logPhi)
+        if logPhi.ndim == 2:
+            logPhi = logPhi[None]
+        count, N, M = logPhi.shape
+        assert M == 3 * N
+        out = np.empty((count, N, 3))
+        self._check(self._lib.bgp_get_phi_host(self._h, count, N, _ptr(logPhi), _ptr(out)), "bgp_get_phi_host")
+        return out
+
+    # ------------------------------------------------------------------ test hooks
+    def debug_set_stop_phase(self, phase):
+        self._check(self._lib.bgp_debug_set_stop_phase(self._h, int(phase)), "bgp_debug_set_stop_phase")
+
+    def debug_matrix(self, N, slot, which, symmetric=False):
+        Mp = self._lib.bgp_debug_padded_size(int(N))
+        out = np.empty((Mp, Mp))
+        self._check(self._lib.bgp_debug_dense_matrix(self._h, int(slot), int(which), int(symmetric), _ptr(out)),
+                    "bgp_debug_dense_matrix")
+        return out
+
+    def debug_vector(self, N, D, slot, which):
+        Mp = self._lib.bgp_debug_padded_size(int(N))
+        n = Mp * (D if which in (2, 3, 4, 5, 6) else 1)
+        out = np.empty(n)
+        self._check(self._lib.bgp_debug_dense_vector(self._h, int(slot), int(which), _ptr(out)), "bgp_debug_dense_vector")
+        return out.reshape(-1, Mp) if which in (2, 3, 4, 5, 6) else out
+
+
+_default_engine = None
+
+
+def default_engine():
+    """Process-wide engine on the GPU named by BGP_DEVICE / LOCAL_RANK (default 0)."""
+    global _default_engine
+    if _default_engine is None:
+        dev = int(os.environ.get("BGP_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_engine = Engine(dev)
+    return _default_engine

@@ -1,0 +1,339 @@
+// extern "C" boundary of libbgp_b200.so (declared in include/branchedgp_b200.h): handle, workspace, wave loop.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/branchedgp_b200.h"
+#include "bgp_launch.h"
+
+using namespace bgp;
+
+struct bgp_handle {
+    int device = 0;
+    int sm_count = 0;
+    int max_slots = 0;         // 0 = default
+    int stop_phase = 0;
+    char err[512] = {0};
+    // workspace (grow-only)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // staging for the _host entry points (grow-only)
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // description of the last dense wave, for the debug readers
+    DenseParams lastP;
+    int last_slots = 0;
+    bool kernels_ready = false;
+};
+
+static int fail(bgp_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(h, BGP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static DenseDims make_dims(int N, int D) {
+    DenseDims d;
+    d.N = N;
+    d.M = 3 * N;
+    d.Mp = (d.M + MB - 1) / MB * MB;
+    d.nT = d.Mp / TS;
+    d.nM = d.Mp / MB;
+    d.D = D;
+    d.nch = (N + PHI_RCH - 1) / PHI_RCH;
+    d.mat_elems = packed_tiles(d.nT) * TILE_ELEMS;
+    d.vec_elems = vec_layout(d.Mp, d.nM, D).total;
+    return d;
+}
+
+struct SlotLayout {   // byte offsets inside one slot
+    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, vec, Apart, vpart, klpart, lse, total;
+};
+static SlotLayout slot_layout(const DenseDims& d) {
+    SlotLayout L;
+    size_t o = 0;
+    auto take = [&](size_t doubles) { size_t r = o; o = align_up(o + doubles * 8, 256); return r; };
+    L.LC = take(d.mat_elems); L.RX = take(d.mat_elems); L.PB = take(d.mat_elems); L.LB = take(d.mat_elems);
+    L.LCe = take((size_t)d.nT * TILE_ELEMS);
+    L.LinvD = take((size_t)d.nM * 16 * TILE_ELEMS);
+    L.RinvD = take((size_t)d.nM * 16 * TILE_ELEMS);
+    L.SCR = take((size_t)2 * 16 * TILE_ELEMS);
+    L.vec = take(d.vec_elems);
+    L.Apart = take((size_t)d.nch * d.Mp);
+    L.vpart = take((size_t)d.nch * d.D * d.Mp);
+    L.klpart = take(d.nch);
+    L.lse = take(d.N);
+    L.total = o;
+    return L;
+}
+
+extern "C" {
+
+int bgp_version(void) { return 100; }
+
+int bgp_create(int device, bgp_handle** out) {
+    if (!out) return BGP_ERR_ARG;
+    bgp_handle* h = new bgp_handle();
+    *out = h;
+    h->device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return fail(h, BGP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU(dense_init_kernels());
+    h->kernels_ready = true;
+    return BGP_OK;
+}
+
+int bgp_destroy(bgp_handle* h) {
+    if (!h) return BGP_OK;
+    cudaSetDevice(h->device);
+    if (h->ws) cudaFree(h->ws);
+    if (h->stage) cudaFree(h->stage);
+    delete h;
+    return BGP_OK;
+}
+
+const char* bgp_last_error(const bgp_handle* h) { return h ? h->err : "null handle"; }
+int bgp_device_sm_count(const bgp_handle* h) { return h ? h->sm_count : 0; }
+int bgp_set_max_slots(bgp_handle* h, int max_slots) {
+    if (!h || max_slots < 0) return BGP_ERR_ARG;
+    h->max_slots = max_slots;
+    return BGP_OK;
+}
+size_t bgp_dense_slot_bytes(int N, int D) { return slot_layout(make_dims(N, D)).total; }
+
+int bgp_host_alloc(void** p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BGP_OK : BGP_ERR_NOMEM; }
+int bgp_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BGP_OK : BGP_ERR_CUDA; }
+
+static int ensure_ws(bgp_handle* h, size_t bytes) {
+    if (h->ws_bytes >= bytes) return BGP_OK;
+    if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
+    cudaError_t e = cudaMalloc(&h->ws, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(h, BGP_ERR_NOMEM, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    h->ws_bytes = bytes;
+    return BGP_OK;
+}
+
+static int pick_slots(bgp_handle* h, int count, size_t slot_bytes) {
+    int cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t avail = free_b + h->ws_bytes;
+        const size_t fit = (size_t)(0.9 * (double)avail) / slot_bytes;
+        if ((size_t)cap > fit) cap = (int)fit;
+    }
+    if (cap > count) cap = count;
+    return cap;
+}
+
+int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
+                        const int* item_gene, const double* b, const double* prior, const double* hyp, int kernel_kind,
+                        int model, double kl_weight, const double* logPhi, const double* KConst, int want_grad,
+                        double* elbo, double* grad_hyp, double* grad_logPhi, int* status, void* cuda_stream) {
+    if (!h) return BGP_ERR_ARG;
+    if (count <= 0 || N <= 0 || D <= 0 || nY <= 0) return fail(h, BGP_ERR_ARG, "count, N, D, nY must be positive");
+    if (!t || !Y || !item_gene || !b || !prior || !hyp || !logPhi || !elbo || !status) return fail(h, BGP_ERR_ARG, "null input pointer");
+    if (want_grad && (!grad_hyp || !grad_logPhi)) return fail(h, BGP_ERR_ARG, "want_grad needs grad_hyp and grad_logPhi");
+    if (kernel_kind != BGP_KERNEL_MATERN32 && kernel_kind != BGP_KERNEL_SQEXP) return fail(h, BGP_ERR_ARG, "unknown kernel kind %d", kernel_kind);
+    if (model != BGP_MODEL_BGP && model != BGP_MODEL_MBGP) return fail(h, BGP_ERR_ARG, "unknown model %d", model);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const DenseDims d = make_dims(N, D);
+    const SlotLayout SL = slot_layout(d);
+    const int slots = pick_slots(h, count, SL.total);
+    if (slots < 1) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d needs %zu bytes of workspace", N, SL.total);
+    int rc = ensure_ws(h, (size_t)slots * SL.total);
+    if (rc != BGP_OK) return rc;
+    char* base = (char*)h->ws;
+    const size_t stride_d = SL.total / 8;   // slot stride in doubles (SL.total is a multiple of 256)
+
+    DenseParams P;
+    memset(&P, 0, sizeof(P));
+    P.d = d;
+    P.kind = kernel_kind;
+    P.model = model;
+    P.square_noise = 1e-6;
+    P.kl_weight = kl_weight;
+    P.t = t; P.hyp = hyp; P.bv = b; P.KConst = KConst;
+    P.LC = (double*)(base + SL.LC); P.RX = (double*)(base + SL.RX); P.PB = (double*)(base + SL.PB); P.LB = (double*)(base + SL.LB);
+    P.LCe = (double*)(base + SL.LCe); P.LinvD = (double*)(base + SL.LinvD); P.RinvD = (double*)(base + SL.RinvD);
+    P.SCR = (double*)(base + SL.SCR); P.vec = (double*)(base + SL.vec);
+    P.status = status; P.elbo = elbo; P.grad_hyp = grad_hyp;
+    P.slot_stride = (long long)stride_d;
+
+    PhiParams F;
+    memset(&F, 0, sizeof(F));
+    F.N = N; F.M = d.M; F.Mp = d.Mp; F.D = D; F.nch = d.nch; F.model = model; F.kl_weight = kl_weight;
+    F.logPhi = logPhi; F.t = t; F.prior = prior; F.bv = b; F.Y = Y; F.item_gene = item_gene;
+    F.lse = (double*)(base + SL.lse); F.Apart = (double*)(base + SL.Apart); F.vpart = (double*)(base + SL.vpart);
+    F.klpart = (double*)(base + SL.klpart);
+    F.slot_stride = (long long)stride_d;
+    const VecLayout VL = vec_layout(d.Mp, d.nM, D);
+    F.Abar = P.vec + VL.Abar; F.vbar = P.vec + VL.vbar;
+    F.grad_logPhi = grad_logPhi;
+
+    for (int item0 = 0; item0 < count; item0 += slots) {
+        const int n = (count - item0 < slots) ? (count - item0) : slots;
+        P.item0 = item0;
+        F.item0 = item0;
+        phi_launch_forward(F, n, st);
+        dense_launch_prep(P, F.Apart, F.vpart, F.klpart, Y, item_gene, n, st);
+        dense_launch_pipeline(P, n, want_grad, h->stop_phase, st);
+        if (want_grad && (h->stop_phase == 0 || h->stop_phase >= 9)) phi_launch_backward(F, n, st);
+        CU(cudaGetLastError());
+        h->last_slots = n;
+    }
+    h->lastP = P;
+    return BGP_OK;
+}
+
+// ---- host-pointer variant ---------------------------------------------------------------------------------------
+static int ensure_stage(bgp_handle* h, size_t bytes) {
+    if (h->stage_bytes >= bytes) return BGP_OK;
+    if (h->stage) { cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
+    cudaError_t e = cudaMalloc(&h->stage, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(h, BGP_ERR_NOMEM, "staging of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    h->stage_bytes = bytes;
+    return BGP_OK;
+}
+
+int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
+                             const int* item_gene, const double* b, const double* prior, const double* hyp,
+                             int kernel_kind, int model, double kl_weight, const double* logPhi, const double* KConst,
+                             int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status) {
+    if (!h) return BGP_ERR_ARG;
+    if (count <= 0 || N <= 0 || D <= 0 || nY <= 0) return fail(h, BGP_ERR_ARG, "count, N, D, nY must be positive");
+    CU(cudaSetDevice(h->device));
+    const size_t M = 3 * (size_t)N;
+    const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
+    // work in chunks so that the staged logPhi / gradient stay bounded
+    const DenseDims d = make_dims(N, D);
+    const SlotLayout SL = slot_layout(d);
+    const size_t per_item = (size_t)N * M * 8;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = free_b + h->ws_bytes + h->stage_bytes;
+    int cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
+    const size_t per_slot_all = SL.total + 2 * per_item;
+    if ((size_t)cap * per_slot_all > (size_t)(0.85 * (double)avail)) cap = (int)((size_t)(0.85 * (double)avail) / per_slot_all);
+    if (cap < 1) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d does not fit in device memory", N);
+    if (cap > count) cap = count;
+    const int saved_slots = h->max_slots;
+    h->max_slots = cap;
+
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t o_t = take((size_t)N * 8), o_Y = take((size_t)nY * N * D * 8), o_prior = take((size_t)N * pcols * 8);
+    const size_t o_K = take(KConst ? M * M * 8 : 0);
+    const size_t o_gene = take((size_t)cap * 4), o_b = take((size_t)cap * 8), o_hyp = take((size_t)cap * 24);
+    const size_t o_elbo = take((size_t)cap * 8), o_gh = take((size_t)cap * 32), o_st = take((size_t)cap * 4);
+    const size_t o_lp = take((size_t)cap * per_item), o_g = take(want_grad ? (size_t)cap * per_item : 0);
+    int rc = ensure_stage(h, o);
+    if (rc != BGP_OK) { h->max_slots = saved_slots; return rc; }
+    char* s = (char*)h->stage;
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(s + o_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s + o_Y, Y, (size_t)nY * N * D * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s + o_prior, prior, (size_t)N * pcols * 8, cudaMemcpyHostToDevice, st));
+    if (KConst) CU(cudaMemcpyAsync(s + o_K, KConst, M * M * 8, cudaMemcpyHostToDevice, st));
+    for (int i0 = 0; i0 < count && rc == BGP_OK; i0 += cap) {
+        const int n = (count - i0 < cap) ? (count - i0) : cap;
+        CU(cudaMemcpyAsync(s + o_gene, item_gene + i0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s + o_b, b + i0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s + o_hyp, hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s + o_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, st));
+        rc = bgp_dense_elbo_grad(h, n, N, D, (double*)(s + o_t), (double*)(s + o_Y), nY, (int*)(s + o_gene), (double*)(s + o_b),
+                                 (double*)(s + o_prior), (double*)(s + o_hyp), kernel_kind, model, kl_weight, (double*)(s + o_lp),
+                                 KConst ? (double*)(s + o_K) : nullptr, want_grad, (double*)(s + o_elbo), (double*)(s + o_gh),
+                                 want_grad ? (double*)(s + o_g) : nullptr, (int*)(s + o_st), st);
+        if (rc != BGP_OK) break;
+        CU(cudaMemcpyAsync(elbo + i0, s + o_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(status + i0, s + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (want_grad) {
+            CU(cudaMemcpyAsync(grad_hyp + (size_t)i0 * 4, s + o_gh, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, s + o_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+    }
+    h->max_slots = saved_slots;
+    return rc;
+}
+
+int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi) {
+    if (!h || count <= 0 || N <= 0 || !logPhi || !phi) return BGP_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    const size_t per_item = (size_t)N * 3 * N * 8;
+    int rc = ensure_stage(h, align_up(per_item, 256) + (size_t)N * 3 * 8);
+    if (rc != BGP_OK) return rc;
+    char* s = (char*)h->stage;
+    for (int i = 0; i < count; ++i) {
+        CU(cudaMemcpyAsync(s, logPhi + (size_t)i * N * 3 * N, per_item, cudaMemcpyHostToDevice, 0));
+        phi_launch_gather((double*)s, (double*)(s + align_up(per_item, 256)), 1, N, 0);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(phi + (size_t)i * N * 3, s + align_up(per_item, 256), (size_t)N * 3 * 8, cudaMemcpyDeviceToHost, 0));
+        CU(cudaStreamSynchronize(0));
+    }
+    return BGP_OK;
+}
+
+// ---- test hooks -------------------------------------------------------------------------------------------------
+int bgp_debug_set_stop_phase(bgp_handle* h, int phase) {
+    if (!h) return BGP_ERR_ARG;
+    h->stop_phase = phase;
+    return BGP_OK;
+}
+int bgp_debug_padded_size(int N) { return make_dims(N, 1).Mp; }
+
+int bgp_debug_dense_matrix(bgp_handle* h, int slot, int which, int symmetric, double* out_host) {
+    if (!h || !out_host || slot < 0 || slot >= h->last_slots) return BGP_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    const DenseParams& P = h->lastP;
+    const double* basep = which == 0 ? P.LC : which == 1 ? P.RX : which == 2 ? P.PB : P.LB;
+    const double* src = basep + (size_t)slot * P.slot_stride;
+    const size_t n = (size_t)P.d.Mp * P.d.Mp;
+    double* tmp = nullptr;
+    CU(cudaMalloc(&tmp, n * 8));
+    dense_unpack(src, tmp, P.d.Mp, symmetric, 0);
+    cudaError_t e = cudaMemcpy(out_host, tmp, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(h, BGP_ERR_CUDA, "debug copy: %s", cudaGetErrorString(e));
+    return BGP_OK;
+}
+
+int bgp_debug_dense_vector(bgp_handle* h, int slot, int which, double* out_host) {
+    if (!h || !out_host || slot < 0 || slot >= h->last_slots) return BGP_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    const DenseParams& P = h->lastP;
+    const VecLayout VL = vec_layout(P.d.Mp, P.d.nM, P.d.D);
+    long long off, len = P.d.Mp;
+    switch (which) {
+        case 0: off = VL.A; break;
+        case 1: off = VL.Delta; break;
+        case 2: off = VL.v; len *= P.d.D; break;
+        case 3: off = VL.z; len *= P.d.D; break;
+        case 4: off = VL.c; len *= P.d.D; break;
+        case 5: off = VL.q; len *= P.d.D; break;
+        case 6: off = VL.vbar; len *= P.d.D; break;
+        case 7: off = VL.delta; break;
+        case 8: off = VL.Abar; break;
+        default: return BGP_ERR_ARG;
+    }
+    CU(cudaMemcpy(out_host, P.vec + (size_t)slot * P.slot_stride + off, (size_t)len * 8, cudaMemcpyDeviceToHost));
+    return BGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,733 @@
+// Dense AssignGP bound + gradient, one CTA per work item (gene x branching point), sm_100a.
+//
+// Restates assigngp_dense.py:151-199 (forward) and the hand-derived adjoint of SURVEY.md App. B.1 as a chain of
+// kernels that all share the tile GEMM core of bgp_gemm.cuh.  A work item owns one workspace slot; kernels of a
+// wave are launched back to back on one stream with grid = items in the wave:
+//
+//   k_prep    A, Delta, v = Phi^T Y (from the Phi pass partials), k(t_i, b) vectors
+//   k_chol<0> Lc = chol(K + 1e-6 I), K generated in the epilogue (branch_kernParamGPflow.py:117-198), left-looking
+//   k_syrk    P = (Lc + eps I)^T Delta (Lc + eps I) + I                      (assigngp_dense.py:165-172)
+//   k_chol<1> R = chol(P), log-det                                            (:173)
+//   k_solve   z = L^T v, c = R^-1 z / s, q = R^-T c                           (:174-181)
+//   k_trtri   X = R^-1 in place;  k_lauum  Pbar = -D/2 X^T X - q q^T / 2
+//   k_trmm    G = L Pbar (lower), Lbar = 2 Delta G + v zbar^T, delta = rowsum(G o L)
+//   k_post    Abar, vbar, d/d likvar, ELBO
+//   k_adj     gather form of the blocked Cholesky adjoint, fused with sum(Ktilde o dK/dtheta)
+#include "bgp_dense.cuh"
+#include "bgp_gemm.cuh"
+#include "bgp_launch.h"
+
+namespace bgp {
+
+#define DENSE_SETUP()                                                                              \
+    extern __shared__ __align__(128) unsigned char smem[];                                         \
+    const int tid = threadIdx.x;                                                                   \
+    const int slot = blockIdx.x;                                                                   \
+    const int item = P.item0 + slot;                                                               \
+    const DenseDims& dm = P.d;                                                                     \
+    const VecLayout VL = vec_layout(dm.Mp, dm.nM, dm.D);                                           \
+    double* const vec = P.vec + (size_t)slot * P.slot_stride;                                       \
+    double* const LC = P.LC + (size_t)slot * P.slot_stride;                                         \
+    double* const RX = P.RX + (size_t)slot * P.slot_stride;                                         \
+    double* const PB = P.PB + (size_t)slot * P.slot_stride;                                         \
+    double* const LB = P.LB + (size_t)slot * P.slot_stride;                                         \
+    double* const LCe = P.LCe + (size_t)slot * P.slot_stride;                                 \
+    double* const LinvD = P.LinvD + (size_t)slot * P.slot_stride;                        \
+    double* const RinvD = P.RinvD + (size_t)slot * P.slot_stride;                        \
+    double* const SCR = P.SCR + (size_t)slot * P.slot_stride;                                \
+    const double ell = P.hyp[(size_t)item * 3 + 0];                                                \
+    const double kvar = P.hyp[(size_t)item * 3 + 1];                                               \
+    const double likvar = P.hyp[(size_t)item * 3 + 2];                                             \
+    (void)tid; (void)vec; (void)LC; (void)RX; (void)PB; (void)LB; (void)LCe; (void)LinvD; (void)RinvD; (void)SCR; \
+    (void)ell; (void)kvar; (void)likvar; (void)VL; (void)smem;
+
+// ------------------------------------------------------------------------------------------------ k_prep
+struct PrepArgs {
+    const double* Apart;      // [slot][nch][Mp]
+    const double* vpart;      // [slot][nch][D][Mp]
+    const double* klpart;     // [slot][nch]
+    const double* Y;          // [nY][N][D]
+    const int* item_gene;     // [count]
+};
+
+__global__ void __launch_bounds__(NTHREADS) k_prep(DenseParams P, PrepArgs Q) {
+    DENSE_SETUP();
+    __shared__ double red[32];
+    const int Mp = dm.Mp, M = dm.M, D = dm.D, nch = dm.nch, N = dm.N;
+    const double b = P.bv[item];
+    for (int j = tid; j < Mp; j += NTHREADS) {
+        double a = 0.0;
+        if (j < M)
+            for (int ch = 0; ch < nch; ++ch) a += Q.Apart[(size_t)slot * P.slot_stride + (size_t)ch * Mp + j];
+        vec[VL.A + j] = a;
+        vec[VL.Delta + j] = a / likvar;
+        for (int d = 0; d < D; ++d) {
+            double s = 0.0;
+            if (j < M)
+                for (int ch = 0; ch < nch; ++ch) s += Q.vpart[(size_t)slot * P.slot_stride + ((size_t)ch * D + d) * Mp + j];
+            vec[VL.v + (size_t)d * Mp + j] = s;
+        }
+        // per-cell kernel vectors against the branching point (cross-covariance factors and their derivatives)
+        double k = 0.0, dl = 0.0, dd = 0.0;
+        if (j < N) kbase_grads(P.t[j] - b, ell, kvar, P.kind, k, dl, dd);
+        vec[VL.ka + j] = k;
+        vec[VL.dkal + j] = dl;
+        vec[VL.dkab + j] = -dd;   // d/db k(t - b) = -k'(t - b)
+    }
+    double kl = 0.0;
+    for (int ch = tid; ch < nch; ch += NTHREADS) kl += Q.klpart[(size_t)slot * P.slot_stride + ch];
+    kl = block_sum(kl, red);
+    const double* Yg = Q.Y + (size_t)Q.item_gene[item] * N * D;
+    double y2 = 0.0;
+    for (int e = tid; e < N * D; e += NTHREADS) y2 += Yg[e] * Yg[e];
+    y2 = block_sum(y2, red);
+    if (tid == 0) {
+        vec[VL.scal + SC_KL] = kl;
+        vec[VL.scal + SC_SUMY2] = y2;
+        vec[VL.scal + SC_LOGDET] = 0.0;
+        P.status[item] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ covariance
+// K[(t,f),(t',f')] for cell-major rows 3*cell + f  (VBHelperFunctions.py:170-194; branch_kernParamGPflow.py:117-198).
+__device__ __forceinline__ double kgen(const DenseParams& P, const double* __restrict__ ka, int gi, int gj, double ell,
+                                       double kvar, double kinv) {
+    const int M = P.d.M;
+    if (gi >= M || gj >= M) return gi == gj ? 1.0 : 0.0;   // identity padding
+    if (P.KConst != nullptr) return P.KConst[(size_t)gi * M + gj];
+    const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
+    double k;
+    if (fi == fj) k = kbase(P.t[ci] - P.t[cj], ell, kvar, P.kind);
+    else k = (ka[ci] * kinv) * ka[cj];
+    if (gi == gj) k += P.square_noise;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------ 128x128 helpers in shared memory
+// In-place lower Cholesky of Dm (row-major, leading dimension DLD).  Non-positive pivots are replaced by 1 and reported.
+__device__ void chol128(double* Dm, int& fail, int base_index) {
+    const int tid = threadIdx.x;
+    for (int j = 0; j < MB; ++j) {
+        __syncthreads();
+        double d = Dm[j * DLD + j];
+        if (!(d > 0.0)) {
+            if (fail == 0) fail = base_index + j + 1;
+            d = 1.0;
+        }
+        const double r = sqrt(d);
+        __syncthreads();
+        if (tid == 0) Dm[j * DLD + j] = r;
+        for (int i = j + 1 + tid; i < MB; i += NTHREADS) Dm[i * DLD + j] /= r;
+        __syncthreads();
+        for (int i = j + 1 + (tid >> 4); i < MB; i += 16) {
+            const double lij = Dm[i * DLD + j];
+            for (int k = j + 1 + (tid & 15); k <= i; k += 16) Dm[i * DLD + k] -= lij * Dm[k * DLD + j];
+        }
+    }
+    __syncthreads();
+}
+
+// In-place inverse of the lower-triangular Dm (upper part ignored / left untouched).
+__device__ void trinv128(double* Dm) {
+    const int tid = threadIdx.x;
+    const int j = tid >> 1, h = tid & 1;
+    for (int i = 0; i < MB; ++i) {
+        const double lii = Dm[i * DLD + i];
+        double s = 0.0;
+        for (int k = j + h; k < i; k += 2) s += Dm[i * DLD + k] * Dm[k * DLD + j];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        const double x = (j < i) ? (-s / lii) : (1.0 / lii);
+        __syncthreads();
+        if (h == 0 && j <= i) Dm[i * DLD + j] = x;
+        __syncthreads();
+    }
+}
+
+// Lower tiles (a >= b) of the 128x128 smem block -> global tiles.  packed != nullptr: block-lower matrix position
+// (4J+a, 4J+b);  block != nullptr: 4x4 tile block.  Upper triangle of diagonal tiles is written as zero.
+// dalt (optional): diagonal tiles with `dadd` added on the diagonal.
+__device__ void store_lower_block(const double* Dm, int J, double* packed, double* block, double* dalt, double dadd) {
+    const int tid = threadIdx.x;
+    for (int a = 0; a < TPM; ++a)
+        for (int b = 0; b <= a; ++b) {
+            double* tp = packed ? packed + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS : nullptr;
+            double* tb = block ? block + (size_t)(a * TPM + b) * TILE_ELEMS : nullptr;
+            double* td = (dalt && a == b) ? dalt + (size_t)(TPM * J + a) * TILE_ELEMS : nullptr;
+            for (int e = tid; e < TILE_ELEMS; e += NTHREADS) {
+                const int i = e >> 5, j = e & 31;
+                double v = Dm[(TS * a + i) * DLD + TS * b + j];
+                if (a == b && j > i) v = 0.0;
+                const int o = tswz(i, j);
+                if (tp) tp[o] = v;
+                if (tb) tb[o] = v;
+                if (td) td[o] = v + ((i == j) ? dadd : 0.0);
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ k_chol
+// SRC == 0: factor K (generated on the fly) into LC, also LCe and LinvD.   SRC == 1: factor P (stored in RX) in place, RinvD, log-det.
+template <int SRC>
+__global__ void __launch_bounds__(NTHREADS, 1) k_chol(DenseParams P) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    double* red = smem_red(smem);
+    double* Dm = pipe.stages;
+    double* dst = SRC == 0 ? LC : RX;
+    double* invD = SRC == 0 ? LinvD : RinvD;
+    const double* ka = vec + VL.ka;
+    const double kinv = 1.0 / (kvar + JITTER);   // inv(k(b,b) + jitter), branch_kernParamGPflow.py:168-189
+    const int nM = dm.nM;
+    int fail = 0;
+    double logdet = 0.0;
+    const Opnd opL = opnd_packed(dst, ACC_ROWK);
+    Acc acc;
+    for (int J = 0; J < nM; ++J) {
+        // ---- diagonal macro block
+        acc_zero(acc);
+        gemm_macro(acc, pipe, opL, TPM * J, opL, TPM * J, 0, TPM * J, nullptr);
+        __syncthreads();   // the ring doubles as the 128x128 scratch from here on
+        acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+            if (it < jt) return;
+            const int gi = it * TS + i, gj = jt * TS + j;
+            double s0, s1;
+            if (SRC == 0) {
+                s0 = kgen(P, ka, gi, gj, ell, kvar, kinv);
+                s1 = kgen(P, ka, gi, gj + 1, ell, kvar, kinv);
+            } else {
+                const double2 p = tile_load2(dst + packed_tile(it, jt) * TILE_ELEMS, i, j);
+                s0 = p.x; s1 = p.y;
+            }
+            double* o = Dm + (gi - MB * J) * DLD + (gj - MB * J);
+            o[0] = s0 - v0;
+            o[1] = s1 - v1;
+        });
+        __syncthreads();
+        chol128(Dm, fail, MB * J);
+        if (SRC == 1) {
+            double l = 0.0;
+            if (tid < MB) { const double r = Dm[tid * DLD + tid]; l = log(r * r); }
+            logdet += block_sum(l, red);
+        }
+        store_lower_block(Dm, J, dst, nullptr, SRC == 0 ? LCe : nullptr, JITTER);
+        __syncthreads();
+        trinv128(Dm);
+        store_lower_block(Dm, J, nullptr, invD + (size_t)J * 16 * TILE_ELEMS, nullptr, 0.0);
+        fence_proxy_async();
+        __syncthreads();
+        // ---- panel below the diagonal block
+        const Opnd opInv = opnd_block(invD + (size_t)J * 16 * TILE_ELEMS, ACC_ROWK, TPM * J, TPM * J, 1);
+        for (int I = J + 1; I < nM; ++I) {
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opL, TPM * I, opL, TPM * J, 0, TPM * J, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                double* tp = dst + packed_tile(it, jt) * TILE_ELEMS;
+                double s0, s1;
+                if (SRC == 0) {
+                    const int gi = it * TS + i, gj = jt * TS + j;
+                    s0 = kgen(P, ka, gi, gj, ell, kvar, kinv);
+                    s1 = kgen(P, ka, gi, gj + 1, ell, kvar, kinv);
+                } else {
+                    const double2 p = tile_load2(tp, i, j);
+                    s0 = p.x; s1 = p.y;
+                }
+                tile_store2(tp, i, j, s0 - v0, s1 - v1);
+            });
+            fence_proxy_async();
+            // X = C * inv(L_JJ)^T, in place
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opL, TPM * I, opInv, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                tile_store2(dst + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
+            });
+            fence_proxy_async();
+        }
+    }
+    if (tid == 0) {
+        if (SRC == 1) vec[VL.scal + SC_LOGDET] = logdet;
+        if (fail != 0 && P.status[item] == 0) P.status[item] = fail + (SRC == 1 ? dm.Mp : 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_syrk:  P = L^T Delta L + I  (L = Lc + eps I)
+__global__ void __launch_bounds__(NTHREADS, 1) k_syrk(DenseParams P) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    const Opnd opL = opnd_packed(LC, ACC_COLK, LCe);
+    const double* Delta = vec + VL.Delta;
+    Acc acc;
+    for (int I = 0; I < dm.nM; ++I)
+        for (int J = 0; J <= I; ++J) {
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opL, TPM * I, opL, TPM * J, TPM * I, dm.nT, Delta);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                if (it < jt) return;
+                const int gi = it * TS + i, gj = jt * TS + j;
+                if (gi == gj) v0 += 1.0;
+                if (gi == gj + 1) v1 += 1.0;
+                tile_store2(RX + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
+            });
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ k_solve: z, c, q
+__global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
+    DENSE_SETUP();
+    __shared__ double part[NTHREADS];
+    __shared__ double yv[MB];
+    __shared__ double red[32];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int Mp = dm.Mp, nT = dm.nT, nM = dm.nM;
+    double sumc2 = 0.0;
+    for (int d = 0; d < dm.D; ++d) {
+        const double* v = vec + VL.v + (size_t)d * Mp;
+        double* z = vec + VL.z + (size_t)d * Mp;
+        double* cv = vec + VL.c + (size_t)d * Mp;
+        double* q = vec + VL.q + (size_t)d * Mp;
+        // z = (Lc + eps I)^T v : z[j] = sum_{i >= j} L[i][j] v[i]
+        for (int jt = warp; jt < nT; jt += NTHREADS / 32) {
+            double s = 0.0;
+            for (int it = jt; it < nT; ++it) {
+                const double* tile = (it == jt) ? LCe + (size_t)it * TILE_ELEMS : LC + packed_tile(it, jt) * TILE_ELEMS;
+                const double* vv = v + it * TS;
+#pragma unroll 8
+                for (int i = 0; i < TS; ++i) s += tile[tswz(i, lane)] * vv[i];
+            }
+            z[jt * TS + lane] = s;
+        }
+        __syncthreads();
+        // forward substitution by macro block rows: cu_J = inv(R_JJ) (z_J - sum_{k<J} R[J,k] cu_k)   (cu = R^-1 z)
+        for (int J = 0; J < nM; ++J) {
+            {
+                const int a = warp & 3, h = warp >> 2;
+                const int it = TPM * J + a;
+                double s = 0.0;
+                for (int kt = h; kt < TPM * J; kt += 2) {
+                    const double* row = RX + packed_tile(it, kt) * TILE_ELEMS + lane * TS;
+                    const double* cc = cv + kt * TS;
+                    const int sw = (lane & 3) << 2;
+#pragma unroll 8
+                    for (int k = 0; k < TS; ++k) s += row[k ^ sw] * cc[k];
+                }
+                part[tid] = s;
+            }
+            __syncthreads();
+            if (tid < MB) yv[tid] = z[MB * J + tid] - part[tid] - part[tid + MB];
+            __syncthreads();
+            if (tid < MB) {
+                const double* blk = RinvD + (size_t)J * 16 * TILE_ELEMS;
+                const int a = tid >> 5, i = tid & 31;
+                double s = 0.0;
+                for (int b = 0; b <= a; ++b) {
+                    const double* row = blk + (size_t)(a * TPM + b) * TILE_ELEMS + i * TS;
+                    const int sw = (i & 3) << 2;
+                    for (int k = 0; k < TS; ++k) s += row[k ^ sw] * yv[b * TS + k];
+                }
+                cv[MB * J + tid] = s;
+            }
+            __syncthreads();
+        }
+        // c = cu / s
+        for (int j = tid; j < Mp; j += NTHREADS) {
+            const double x = cv[j] / likvar;
+            cv[j] = x;
+            sumc2 += x * x;
+        }
+        __syncthreads();
+        // backward substitution: q_J = inv(R_JJ)^T (c_J - sum_{I>J} R[I,J]^T q_I)
+        for (int J = nM - 1; J >= 0; --J) {
+            {
+                const int b = warp & 3, h = warp >> 2;
+                const int jt = TPM * J + b;
+                double s = 0.0;
+                for (int it = TPM * (J + 1) + h; it < nT; it += 2) {
+                    const double* tile = RX + packed_tile(it, jt) * TILE_ELEMS;
+                    const double* qq = q + it * TS;
+#pragma unroll 8
+                    for (int i = 0; i < TS; ++i) s += tile[tswz(i, lane)] * qq[i];
+                }
+                part[tid] = s;
+            }
+            __syncthreads();
+            if (tid < MB) yv[tid] = cv[MB * J + tid] - part[tid] - part[tid + MB];
+            __syncthreads();
+            if (tid < MB) {
+                const double* blk = RinvD + (size_t)J * 16 * TILE_ELEMS;
+                const int b = tid >> 5, j = tid & 31;
+                double s = 0.0;
+                for (int a = b; a < TPM; ++a) {
+                    const double* tile = blk + (size_t)(a * TPM + b) * TILE_ELEMS;
+                    for (int k = 0; k < TS; ++k) s += tile[tswz(k, j)] * yv[a * TS + k];
+                }
+                q[MB * J + tid] = s;
+            }
+            __syncthreads();
+        }
+    }
+    sumc2 = block_sum(sumc2, red);
+    if (tid == 0) vec[VL.scal + SC_SUMC2] = sumc2;
+}
+
+// ------------------------------------------------------------------------------------------------ k_trtri:  RX <- inv(R), in place
+__global__ void __launch_bounds__(NTHREADS, 1) k_trtri(DenseParams P) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    const int nM = dm.nM;
+    const Opnd opRow = opnd_packed(RX, ACC_ROWK);
+    const Opnd opCol = opnd_packed(RX, ACC_COLK);
+    Acc acc;
+    for (int J = nM - 1; J >= 0; --J) {
+        const double* blk = RinvD + (size_t)J * 16 * TILE_ELEMS;
+        const Opnd opInv = opnd_block(blk, ACC_COLK, TPM * J, TPM * J, 1);
+        for (int I = nM - 1; I > J; --I) {
+            // acc = sum_{J<k<=I} X[I,k] R[k,J]
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opRow, TPM * I, opCol, TPM * J, TPM * (J + 1), TPM * I + TPM, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                tile_store2(RX + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
+            });
+            fence_proxy_async();
+            // X[I,J] = -acc * inv(R_JJ)
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opRow, TPM * I, opInv, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                tile_store2(RX + packed_tile(it, jt) * TILE_ELEMS, i, j, -v0, -v1);
+            });
+            fence_proxy_async();
+        }
+        // X[J,J] = inv(R_JJ)
+        __syncthreads();
+        for (int a = 0; a < TPM; ++a)
+            for (int b = 0; b <= a; ++b) {
+                const double* src = blk + (size_t)(a * TPM + b) * TILE_ELEMS;
+                double* dstp = RX + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS;
+                for (int e = tid; e < TILE_ELEMS; e += NTHREADS) dstp[e] = src[e];
+            }
+        fence_proxy_async();
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_lauum:  PB = -D/2 X^T X - 1/2 q q^T
+__global__ void __launch_bounds__(NTHREADS, 1) k_lauum(DenseParams P) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    const Opnd opX = opnd_packed(RX, ACC_COLK);
+    const double* q = vec + VL.q;
+    const int Mp = dm.Mp, D = dm.D;
+    const double hD = 0.5 * (double)D;
+    Acc acc;
+    for (int I = 0; I < dm.nM; ++I)
+        for (int J = 0; J <= I; ++J) {
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opX, TPM * I, opX, TPM * J, TPM * I, dm.nT, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                if (it < jt) return;
+                const int gi = it * TS + i, gj = jt * TS + j;
+                double qq0 = 0.0, qq1 = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    const double qi = q[(size_t)d * Mp + gi];
+                    qq0 += qi * q[(size_t)d * Mp + gj];
+                    qq1 += qi * q[(size_t)d * Mp + gj + 1];
+                }
+                tile_store2(PB + packed_tile(it, jt) * TILE_ELEMS, i, j, -hD * v0 - 0.5 * qq0, -hD * v1 - 0.5 * qq1);
+            });
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ k_trmm:  G = L Pbar (lower), Lbar, delta partials
+__global__ void __launch_bounds__(NTHREADS, 1) k_trmm(DenseParams P) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    double* red = smem_red(smem);
+    const Opnd opL = opnd_packed(LC, ACC_ROWK, LCe);
+    const Opnd opP = opnd_packed(PB, ACC_SYM);
+    const double* Delta = vec + VL.Delta;
+    const double* v = vec + VL.v;
+    const double* q = vec + VL.q;
+    double* dpart = vec + VL.dpart;
+    const int Mp = dm.Mp, D = dm.D;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    Acc acc;
+    for (int I = 0; I < dm.nM; ++I)
+        for (int J = 0; J <= I; ++J) {
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opL, TPM * I, opP, TPM * J, 0, TPM * I + TPM, nullptr);
+            double rs[4] = {0.0, 0.0, 0.0, 0.0};
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                if (it < jt) return;
+                const int gi = it * TS + i, gj = jt * TS + j;
+                const double* lt = (it == jt) ? LCe + (size_t)it * TILE_ELEMS : LC + packed_tile(it, jt) * TILE_ELEMS;
+                const double2 l = tile_load2(lt, i, j);
+                double vz0 = 0.0, vz1 = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    const double vi = v[(size_t)d * Mp + gi];
+                    vz0 += vi * q[(size_t)d * Mp + gj];
+                    vz1 += vi * q[(size_t)d * Mp + gj + 1];
+                }
+                const double dl = 2.0 * Delta[gi];
+                double o0 = 0.0, o1 = 0.0, r = 0.0;
+                if (gi >= gj) { o0 = dl * v0 + vz0 / likvar; r += v0 * l.x; }
+                if (gi >= gj + 1) { o1 = dl * v1 + vz1 / likvar; r += v1 * l.y; }
+                rs[i >> 3] += r;
+                tile_store2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j, o0, o1);
+            });
+            // delta partial of this macro tile: row sums over its 128 columns
+            __syncthreads();
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                double r = rs[mi];
+                r += __shfl_xor_sync(0xffffffffu, r, 1);
+                r += __shfl_xor_sync(0xffffffffu, r, 2);
+                if (c == 0) red[(warp >> 2) * MB + (warp & 3) * TS + 8 * mi + g] = r;
+            }
+            __syncthreads();
+            if (tid < MB) dpart[(size_t)J * Mp + MB * I + tid] = red[tid] + red[MB + tid];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ k_post: delta, Abar, vbar, d/d likvar, ELBO
+__global__ void __launch_bounds__(NTHREADS) k_post(DenseParams P) {
+    DENSE_SETUP();
+    __shared__ double red[32];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int Mp = dm.Mp, M = dm.M, nT = dm.nT, D = dm.D, N = dm.N;
+    double adel = 0.0;
+    for (int i = tid; i < Mp; i += NTHREADS) {
+        const int I = i / MB;
+        double s = 0.0;
+        for (int J = 0; J <= I; ++J) s += vec[VL.dpart + (size_t)J * Mp + i];
+        vec[VL.delta + i] = s;
+        vec[VL.Abar + i] = s / likvar;
+        if (i < M) adel += vec[VL.A + i] * s;
+    }
+    adel = block_sum(adel, red);
+    // vbar = L zbar,  zbar = q / s :  vbar[i] = sum_{j <= i} L[i][j] q[j] / s
+    for (int d = 0; d < D; ++d) {
+        const double* q = vec + VL.q + (size_t)d * Mp;
+        double* vb = vec + VL.vbar + (size_t)d * Mp;
+        for (int it = warp; it < nT; it += NTHREADS / 32) {
+            double s = 0.0;
+            const int sw = (lane & 3) << 2;
+            for (int jt = 0; jt <= it; ++jt) {
+                const double* row = ((it == jt) ? LCe + (size_t)it * TILE_ELEMS : LC + packed_tile(it, jt) * TILE_ELEMS) + lane * TS;
+                const double* qq = q + jt * TS;
+#pragma unroll 8
+                for (int k = 0; k < TS; ++k) s += row[k ^ sw] * qq[k];
+            }
+            vb[it * TS + lane] = s / likvar;
+        }
+    }
+    if (tid == 0) {
+        const double s = likvar;
+        const double ND = (double)N * (double)D;
+        const double logdet = vec[VL.scal + SC_LOGDET], c2 = vec[VL.scal + SC_SUMC2], kl = vec[VL.scal + SC_KL],
+                     y2 = vec[VL.scal + SC_SUMY2];
+        // assigngp_dense.py:184-199
+        const double a1 = -0.5 * ND * log(2.0 * 3.14159265358979323846 * s);
+        const double a2 = -0.5 * (double)D * logdet;
+        const double a3 = -0.5 * y2 / s;
+        const double a4 = 0.5 * c2;
+        P.elbo[item] = a1 + a2 + a3 + a4 - P.kl_weight * kl;
+        P.grad_hyp[(size_t)item * 4 + 2] = -0.5 * ND / s + 0.5 * y2 / (s * s) - c2 / s - adel / (s * s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_adj
+// sum over the stored lower triangle of Ktilde o dK/dtheta.  w carries 2*Kbar_ij off the diagonal and Kbar_ii on it.
+__device__ __forceinline__ void hyper_accum(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ dkal,
+                                            const double* __restrict__ dkab, int gi, int gj, double w, double ell, double kvar,
+                                            double kinv, double& gl, double& gv, double& gb) {
+    const int M = P.d.M;
+    if (gi >= M || gj >= M || gj > gi) return;
+    if (gi == gj) w *= 0.5;
+    const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
+    if (fi == fj) {
+        double k, dl, dd;
+        kbase_grads(P.t[ci] - P.t[cj], ell, kvar, P.kind, k, dl, dd);
+        gl += w * dl;
+        gv += w * k / kvar;
+    } else {
+        const double a = ka[ci], b = ka[cj];
+        const double cr = (a * kinv) * b;
+        gl += w * (dkal[ci] * b + a * dkal[cj]) * kinv;
+        gv += w * cr * (2.0 / kvar - kinv);
+        gb += w * (dkab[ci] * b + a * dkab[cj]) * kinv;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_adj(DenseParams P) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    double* red = smem_red(smem);
+    const int nM = dm.nM, nT = dm.nT;
+    const double* ka = vec + VL.ka;
+    const double* dkal = vec + VL.dkal;
+    const double* dkab = vec + VL.dkab;
+    const double kinv = 1.0 / (kvar + JITTER);
+    const bool want_hyp = (P.KConst == nullptr);
+    double gl = 0.0, gv = 0.0, gb = 0.0;
+    const Opnd opAsym = opnd_packed(LB, ACC_SYM);
+    const Opnd opArow = opnd_packed(LB, ACC_ROWK);
+    const Opnd opAcol = opnd_packed(LB, ACC_COLK);
+    const Opnd opLcol = opnd_packed(LC, ACC_COLK);
+    double* S0 = SCR;
+    double* S1 = SCR + 16 * TILE_ELEMS;
+    Acc acc;
+    for (int J = nM - 1; J >= 0; --J) {
+        const double* blk = LinvD + (size_t)J * 16 * TILE_ELEMS;
+        const Opnd opInvCol = opnd_block(blk, ACC_COLK, TPM * J, TPM * J, 1);
+        for (int I = nM - 1; I > J; --I) {
+            // E = Lbar[I,J] - sum_{k>J} Atilde_full[I,k] Lc[k,J]
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * (J + 1), nT, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                double* tp = LB + packed_tile(it, jt) * TILE_ELEMS;
+                const double2 l = tile_load2(tp, i, j);
+                tile_store2(tp, i, j, l.x - v0, l.y - v1);
+            });
+            fence_proxy_async();
+            // Atilde[I,J] = E inv(L_JJ)
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opArow, TPM * I, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                tile_store2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
+                if (want_hyp) {
+                    const int gi = it * TS + i, gj = jt * TS + j;
+                    hyper_accum(P, ka, dkal, dkab, gi, gj, v0, ell, kvar, kinv, gl, gv, gb);
+                    hyper_accum(P, ka, dkal, dkab, gi, gj + 1, v1, ell, kvar, kinv, gl, gv, gb);
+                }
+            });
+            fence_proxy_async();
+        }
+        // ---- diagonal block:  Leff = tril(Lbar_JJ) - tril(sum_{I>J} Atilde[I,J]^T Lc[I,J])
+        acc_zero(acc);
+        gemm_macro(acc, pipe, opAcol, TPM * J, opLcol, TPM * J, TPM * (J + 1), nT, nullptr);
+        acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+            const int a = it - TPM * J, b = jt - TPM * J;
+            double o0 = 0.0, o1 = 0.0;
+            if (it >= jt) {
+                const double2 l = tile_load2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j);
+                const int gi = it * TS + i, gj = jt * TS + j;
+                if (gi >= gj) o0 = l.x - v0;
+                if (gi >= gj + 1) o1 = l.y - v1;
+            }
+            tile_store2(S0 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, o0, o1);
+        });
+        fence_proxy_async();
+        // U = Phi(L_JJ^T Leff)
+        acc_zero(acc);
+        gemm_macro(acc, pipe, opLcol, TPM * J, opnd_block(S0, ACC_COLK, TPM * J, TPM * J, 0), TPM * J, TPM * J, TPM * J + TPM, nullptr);
+        acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+            const int a = it - TPM * J, b = jt - TPM * J;
+            const int gi = it * TS + i, gj = jt * TS + j;
+            const double o0 = (gi > gj) ? v0 : (gi == gj ? 0.5 * v0 : 0.0);
+            const double o1 = (gi > gj + 1) ? v1 : (gi == gj + 1 ? 0.5 * v1 : 0.0);
+            tile_store2(S1 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, o0, o1);
+        });
+        fence_proxy_async();
+        // V = inv(L_JJ)^T U
+        acc_zero(acc);
+        gemm_macro(acc, pipe, opInvCol, TPM * J, opnd_block(S1, ACC_COLK, TPM * J, TPM * J, 0), TPM * J, TPM * J, TPM * J + TPM, nullptr);
+        acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+            const int a = it - TPM * J, b = jt - TPM * J;
+            tile_store2(S0 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, v0, v1);
+        });
+        fence_proxy_async();
+        // S = V inv(L_JJ)
+        acc_zero(acc);
+        gemm_macro(acc, pipe, opnd_block(S0, ACC_ROWK, TPM * J, TPM * J, 0), TPM * J, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+        acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+            const int a = it - TPM * J, b = jt - TPM * J;
+            tile_store2(S1 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, v0, v1);
+        });
+        __syncthreads();
+        // Atilde_JJ = S + S^T  (diagonal tiles stored fully symmetric)
+        for (int a = 0; a < TPM; ++a)
+            for (int b = 0; b <= a; ++b) {
+                const double* sab = S1 + (size_t)(a * TPM + b) * TILE_ELEMS;
+                const double* sba = S1 + (size_t)(b * TPM + a) * TILE_ELEMS;
+                double* tp = LB + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS;
+                for (int e = tid; e < TILE_ELEMS; e += NTHREADS) {
+                    const int i = e >> 5, j = e & 31;
+                    const double w = sab[tswz(i, j)] + sba[tswz(j, i)];
+                    tp[tswz(i, j)] = w;
+                    if (want_hyp) hyper_accum(P, ka, dkal, dkab, (TPM * J + a) * TS + i, (TPM * J + b) * TS + j, w, ell, kvar, kinv, gl, gv, gb);
+                }
+            }
+        fence_proxy_async();
+        __syncthreads();
+    }
+    gl = block_sum(gl, red);
+    gv = block_sum(gv, red);
+    gb = block_sum(gb, red);
+    if (tid == 0) {
+        P.grad_hyp[(size_t)item * 4 + 0] = gl;
+        P.grad_hyp[(size_t)item * 4 + 1] = gv;
+        P.grad_hyp[(size_t)item * 4 + 3] = gb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ debug: unpack a tile matrix to row-major
+__global__ void k_unpack(const double* packed, double* out, int Mp, int symmetric) {
+    const int nT = Mp / TS;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)Mp * Mp; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / Mp), j = (int)(e % Mp);
+        const int it = i / TS, jt = j / TS;
+        double v = 0.0;
+        if (it >= jt) v = packed[packed_tile(it, jt) * TILE_ELEMS + tswz(i % TS, j % TS)];
+        else if (symmetric) v = packed[packed_tile(jt, it) * TILE_ELEMS + tswz(j % TS, i % TS)];
+        (void)nT;
+        out[e] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host launchers
+static cudaError_t set_smem(const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); }
+
+cudaError_t dense_init_kernels() {
+    cudaError_t e;
+    if ((e = set_smem((const void*)k_chol<0>)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_chol<1>)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_syrk)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_trtri)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_lauum)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_trmm)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_adj)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+void dense_launch_prep(const DenseParams& P, const double* Apart, const double* vpart, const double* klpart, const double* Y,
+                       const int* item_gene, int nitems, cudaStream_t st) {
+    PrepArgs Q{Apart, vpart, klpart, Y, item_gene};
+    k_prep<<<nitems, NTHREADS, 0, st>>>(P, Q);
+}
+
+// stop_phase > 0 stops after that phase (test hook); want_grad = 0 computes the bound only.
+void dense_launch_pipeline(const DenseParams& P, int nitems, int want_grad, int stop_phase, cudaStream_t st) {
+    const int last = stop_phase > 0 ? stop_phase : 99;
+    if (last >= 1) k_chol<0><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (last >= 2) k_syrk<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (last >= 3) k_chol<1><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (last >= 4) k_solve<<<nitems, NTHREADS, 0, st>>>(P);
+    if (want_grad) {
+        if (last >= 5) k_trtri<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+        if (last >= 6) k_lauum<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+        if (last >= 7) k_trmm<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+    }
+    if (last >= 8) k_post<<<nitems, NTHREADS, 0, st>>>(P);
+    if (want_grad && last >= 9) k_adj<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+}
+
+void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st) {
+    k_unpack<<<296, 256, 0, st>>>(packed, out, Mp, symmetric);
+}
+
+}  // namespace bgp

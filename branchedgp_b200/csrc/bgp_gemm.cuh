@@ -1,0 +1,216 @@
+// Per-CTA fp64 tile GEMM core:  C(128x128, registers) += Aop(128 x k) * Bop(128 x k)^T
+//
+// * operands are streamed from HBM/L2 as 32x32 swizzled tiles by cp.async.bulk (TMA) into a 3-stage shared-memory
+//   ring, completion signalled on mbarriers (expect_tx);
+// * 8 warps, warp tile 32 x 64, mma.sync.aligned.m8n8k4.f64 (DMMA) -- tcgen05 has no fp64 kind;
+// * each logical operand is "outer x k" and is resolved tile by tile from a block-lower matrix in one of three
+//   ways (ROWK: op[o][k] = Mat[o][k];  COLK: op[o][k] = Mat[k][o];  SYM: symmetric matrix stored lower), so every
+//   heavy phase of the dense pipeline (potrf, L^T D L, trtri, lauum, trmm, Cholesky adjoint) is this one routine
+//   with a different operand description, k-range and epilogue.
+#pragma once
+#include "bgp_common.cuh"
+
+namespace bgp {
+
+enum { ACC_ROWK = 0, ACC_COLK = 1, ACC_SYM = 2 };
+enum { LAY_PACKED = 0, LAY_BLOCK = 1 };
+
+struct Opnd {
+    const double* base;   // tile storage
+    const double* dalt;   // optional replacement for the diagonal tiles (packed layout): tile r at dalt + r*1024
+    int layout;           // LAY_PACKED: global block-lower matrix;  LAY_BLOCK: 4x4 tile block, tile (r,c) at (r-r0)*4+(c-c0)
+    int access;           // ACC_*
+    int r0, c0;           // origin of a LAY_BLOCK operand, in tiles
+    int lower;            // tiles with r < c are structural zeros (never loaded, MMAs skipped)
+};
+
+__device__ __forceinline__ Opnd opnd_packed(const double* base, int access, const double* dalt = nullptr) {
+    Opnd o;
+    o.base = base; o.dalt = dalt; o.layout = LAY_PACKED; o.access = access; o.r0 = 0; o.c0 = 0; o.lower = 1;
+    return o;
+}
+__device__ __forceinline__ Opnd opnd_block(const double* base, int access, int r0, int c0, int lower) {
+    Opnd o;
+    o.base = base; o.dalt = nullptr; o.layout = LAY_BLOCK; o.access = access; o.r0 = r0; o.c0 = c0; o.lower = lower;
+    return o;
+}
+
+// Tile that holds op[o-tile][k-tile]; `trans` tells whether the tile is stored [k][o] (true) or [o][k] (false).
+__device__ __forceinline__ const double* resolve(const Opnd& op, int o, int kt, bool& trans) {
+    int r, c;
+    if (op.access == ACC_ROWK) { r = o; c = kt; trans = false; }
+    else if (op.access == ACC_COLK) { r = kt; c = o; trans = true; }
+    else if (o >= kt) { r = o; c = kt; trans = false; }
+    else { r = kt; c = o; trans = true; }
+    if (op.lower && r < c) return nullptr;
+    if (op.layout == LAY_PACKED) {
+        if (r == c && op.dalt != nullptr) return op.dalt + (size_t)r * TILE_ELEMS;
+        return op.base + packed_tile(r, c) * TILE_ELEMS;
+    }
+    return op.base + (size_t)((r - op.r0) * TPM + (c - op.c0)) * TILE_ELEMS;
+}
+
+struct Pipe {
+    double* stages;    // NSTAGES * STAGE_ELEMS doubles of shared memory
+    uint64_t* full;    // NSTAGES mbarriers
+    uint32_t it;       // running k-step counter; identical in every thread of the CTA
+};
+
+__device__ __forceinline__ void pipe_init(Pipe& p, unsigned char* smem) {
+    p.stages = reinterpret_cast<double*>(smem);
+    p.full = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES + SMEM_RED_DOUBLES * 8);
+    p.it = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGES; ++s) mbar_init(p.full + s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ double* smem_red(unsigned char* smem) { return reinterpret_cast<double*>(smem + PIPE_BYTES); }
+
+typedef double Acc[4][8][2];
+
+__device__ __forceinline__ void acc_zero(Acc& acc) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+}
+
+// One 32-wide k-step of the warp tile.  nmask bit h enables the h-th 32-column half of the warp's 64 columns.
+template <bool TA, bool TB>
+__device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ As, const double* __restrict__ Bs0,
+                                           const double* __restrict__ Bs1, int nmask, const double* __restrict__ ksc,
+                                           int g, int c) {
+    const int g3 = (g & 3) << 2;
+    const int c2 = c << 2;
+    // lane-dependent parts of the swizzled addresses
+    //   non-transposed  tile[8*o8+g][4*k4+c]  ->  (8*o8+g)*32 + (((4*k4) ^ g3) + c)
+    //   transposed      tile[4*k4+c][8*o8+g]  ->  (4*k4+c)*32 + ((8*o8+g) ^ c2)
+    const int nbase = g * TS + c;
+    const int tbase = c * TS;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        double af[4], bf[8];
+        const int kx = ((4 * k4) ^ g3);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int off = TA ? (tbase + 4 * k4 * TS + ((8 * mi + g) ^ c2)) : (nbase + 8 * mi * TS + kx);
+            af[mi] = As[off];
+        }
+        if (ksc != nullptr) {
+            const double s = ksc[4 * k4 + c];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) af[mi] *= s;
+        }
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+            const int o8 = ni & 3;
+            const double* Bt = (ni >> 2) ? Bs1 : Bs0;
+            const int off = TB ? (tbase + 4 * k4 * TS + ((8 * o8 + g) ^ c2)) : (nbase + 8 * o8 * TS + kx);
+            bf[ni] = (nmask & (1 << (ni >> 2))) ? Bt[off] : 0.0;
+        }
+        if (nmask & 1) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+        if (nmask & 2) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 4; ni < 8; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+    }
+}
+
+// acc += Aop[ao0*32 .. +128][kt0*32 .. kt1*32) * Bop[bo0*32 .. +128][same k]^T, optionally with the k index scaled
+// by kscale[k].  Must be called by all NTHREADS threads with identical arguments.
+__device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, int ao0, const Opnd& B, int bo0, int kt0,
+                                           int kt1, const double* __restrict__ kscale) {
+    const int nk = kt1 - kt0;
+    if (nk <= 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, c = lane & 3;
+    const int wa = warp & 3, wb = (warp >> 2) * 2;
+
+    auto issue = [&](int ks) {
+        const uint32_t it = pipe.it + (uint32_t)ks;
+        const int st = (int)(it % NSTAGES);
+        double* sb = pipe.stages + (size_t)st * STAGE_ELEMS;
+        uint64_t* bar = pipe.full + st;
+        const int kt = kt0 + ks;
+        const double* src[8];
+        uint32_t n = 0;
+        bool tr;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { src[a] = resolve(A, ao0 + a, kt, tr); n += (src[a] != nullptr); }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { src[4 + b] = resolve(B, bo0 + b, kt, tr); n += (src[4 + b] != nullptr); }
+        mbar_arrive_expect_tx(bar, n * (uint32_t)TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (src[i] != nullptr) tma_load_1d(sb + (size_t)i * TILE_ELEMS, src[i], TILE_BYTES, bar);
+    };
+
+    __syncthreads();   // every warp is done with the ring (previous GEMM or scratch use)
+    if (tid == 0) {
+        const int pre = nk < (NSTAGES - 1) ? nk : (NSTAGES - 1);
+        for (int p = 0; p < pre; ++p) issue(p);
+    }
+    for (int ks = 0; ks < nk; ++ks) {
+        if (ks + NSTAGES - 1 < nk) {
+            __syncthreads();   // slot (ks-1)%NSTAGES has been consumed by every warp
+            if (tid == 0) issue(ks + NSTAGES - 1);
+        }
+        const uint32_t it = pipe.it + (uint32_t)ks;
+        const int st = (int)(it % NSTAGES);
+        mbar_wait(pipe.full + st, (it / NSTAGES) & 1u);
+        const int kt = kt0 + ks;
+        bool ta, tb0, tb1;
+        const double* pa = resolve(A, ao0 + wa, kt, ta);
+        const double* pb0 = resolve(B, bo0 + wb, kt, tb0);
+        const double* pb1 = resolve(B, bo0 + wb + 1, kt, tb1);
+        if (pa == nullptr) continue;
+        int nmask = (pb0 != nullptr ? 1 : 0) | (pb1 != nullptr ? 2 : 0);
+        if (nmask == 0) continue;
+        const double* sb = pipe.stages + (size_t)st * STAGE_ELEMS;
+        const double* As = sb + (size_t)wa * TILE_ELEMS;
+        const double* Bs0 = sb + (size_t)(4 + wb) * TILE_ELEMS;
+        const double* Bs1 = Bs0 + TILE_ELEMS;
+        const double* ksc = kscale ? kscale + (size_t)kt * TS : nullptr;
+        if (nmask == 3 && tb0 != tb1) {   // the two column halves need different orientations (SYM operand crossing its diagonal)
+            if (ta) { if (tb0) warp_kstep<true, true>(acc, As, Bs0, Bs1, 1, ksc, g, c); else warp_kstep<true, false>(acc, As, Bs0, Bs1, 1, ksc, g, c); }
+            else    { if (tb0) warp_kstep<false, true>(acc, As, Bs0, Bs1, 1, ksc, g, c); else warp_kstep<false, false>(acc, As, Bs0, Bs1, 1, ksc, g, c); }
+            nmask = 2;
+        }
+        const bool tb = (nmask & 1) ? tb0 : tb1;
+        if (ta) { if (tb) warp_kstep<true, true>(acc, As, Bs0, Bs1, nmask, ksc, g, c); else warp_kstep<true, false>(acc, As, Bs0, Bs1, nmask, ksc, g, c); }
+        else    { if (tb) warp_kstep<false, true>(acc, As, Bs0, Bs1, nmask, ksc, g, c); else warp_kstep<false, false>(acc, As, Bs0, Bs1, nmask, ksc, g, c); }
+    }
+    pipe.it += (uint32_t)nk;
+}
+
+// Visit every accumulator pair of the calling thread: f(tile_row, tile_col, i_in_tile, j_in_tile (even), v0, v1)
+// for elements (i, j) and (i, j+1) of tile (4*I + ..., 4*J + ...).
+template <class F>
+__device__ __forceinline__ void acc_foreach(Acc& acc, int I, int J, F f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, c = lane & 3;
+    const int wa = warp & 3, wb = (warp >> 2) * 2;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            f(TPM * I + wa, TPM * J + wb + (ni >> 2), 8 * mi + g, 8 * (ni & 3) + 2 * c, acc[mi][ni][0], acc[mi][ni][1]);
+}
+
+__device__ __forceinline__ void tile_store2(double* tile, int i, int j, double v0, double v1) {
+    *reinterpret_cast<double2*>(tile + tswz(i, j)) = make_double2(v0, v1);
+}
+__device__ __forceinline__ double2 tile_load2(const double* tile, int i, int j) {
+    return *reinterpret_cast<const double2*>(tile + tswz(i, j));
+}
+
+}  // namespace bgp

@@ -1,0 +1,34 @@
+// Parameters of the assignment (Phi) passes shared by the dense, sparse and MBGP pipelines.
+#pragma once
+#include "bgp_common.cuh"
+
+namespace bgp {
+
+constexpr int PHI_RCH = 16;   // rows of logPhi handled by one CTA of the forward pass
+
+struct PhiParams {
+    int N, M, Mp, D, nch, model;
+    int item0;
+    long long slot_stride;     // doubles between consecutive slots for lse / Apart / vpart / klpart / Abar / vbar
+    double kl_weight;
+    const double* logPhi;      // [count][N][M] row-major (M = 3N, cell-major columns 3*cell + f)
+    const double* t;           // [N] pseudotime
+    const double* prior;       // BGP: [N][2] phiPrior;  MBGP: [N][3]
+    const double* bv;          // [count] branching point used for the trunk / branch split (t <= b  => trunk)
+    const double* Y;           // [nY][N][D]
+    const int* item_gene;      // [count]
+    double* lse;               // [slot][N]  row log-sum-exp of logPhi
+    // forward outputs (per slot, partial over row chunks; reduced by the consumer in a fixed order => deterministic)
+    double* Apart;             // [slot][nch][Mp]
+    double* vpart;             // [slot][nch][D][Mp]
+    double* klpart;            // [slot][nch]
+    // backward inputs (per slot) and output
+    const double* Abar;        // [Mp]
+    const double* vbar;        // [D][Mp]
+    double* grad_logPhi;       // [count][N][M]
+};
+
+void phi_launch_forward(const PhiParams& P, int nitems, cudaStream_t st);
+void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st);
+
+}  // namespace bgp

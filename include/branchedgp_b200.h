@@ -1,0 +1,104 @@
+/* branchedgp_b200 -- C ABI of the B200-native evaluator for the BranchedGP hot path.
+ *
+ * The reference (ManchesterBioinference/BranchedGP, pure Python on TensorFlow/GPflow) has no FFI of its own; the
+ * boundary this library sits behind is the Python call the L-BFGS driver makes once per function evaluation:
+ *
+ *   AssignGP.maximum_log_likelihood_objective()            BranchedGP/assigngp_dense.py:151-199   (+ TF autodiff)
+ *   AssignGPSparse.maximum_log_likelihood_objective()      BranchedGP/assigngp_denseSparse.py:59-107
+ *   MBGP AssignGP._build_likelihood_sparse / _single_b     BranchedGP/MBGP/assigngp.py:492-558, 608-647
+ *   AssignGP.GetPhi()                                      BranchedGP/assigngp_dense.py:130-140
+ *
+ * Each entry point evaluates the bound (and its gradient) for `count` independent work items
+ * (gene g, branching point b, hyper-parameters, logPhi) in one call.  Conventions:
+ *   - all reals are IEEE float64, row-major; `M = 3*N` columns of logPhi are cell-major (column 3*cell + f), the
+ *     order produced by VBHelperFunctions.GetFunctionIndexListGeneral (VBHelperFunctions.py:170-194);
+ *   - pointers of the plain entry points are DEVICE pointers owned by the caller; the `_host` variants take HOST
+ *     pointers and do the host<->device copies themselves; the library owns only its workspace;
+ *   - return value 0 = success, otherwise an error code (bgp_last_error gives the text); never throws;
+ *   - status[i] = 0, or k>0 when the Cholesky of item i met a non-positive pivot at row k (<= Mp: K, > Mp: P),
+ *     which the Python layer turns into the exception the reference gets from tf.linalg.cholesky;
+ *   - one handle per (GPU, host thread); calls on one handle are serialised on the given CUDA stream.
+ */
+#ifndef BRANCHEDGP_B200_H
+#define BRANCHEDGP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bgp_handle bgp_handle;
+
+enum { BGP_KERNEL_MATERN32 = 0, BGP_KERNEL_SQEXP = 1 };   /* gpflow.kernels.Matern32 / SquaredExponential */
+enum { BGP_MODEL_BGP = 0, BGP_MODEL_MBGP = 1 };           /* assigngp_dense.AssignGP / MBGP.assigngp.AssignGP (multi=False) */
+
+enum {
+    BGP_OK = 0,
+    BGP_ERR_CUDA = 1,         /* a CUDA runtime call failed */
+    BGP_ERR_ARG = 2,          /* invalid argument */
+    BGP_ERR_NOMEM = 3         /* workspace does not fit in device memory */
+};
+
+int bgp_version(void);
+int bgp_create(int device, bgp_handle** out);
+int bgp_destroy(bgp_handle* h);
+const char* bgp_last_error(const bgp_handle* h);
+int bgp_device_sm_count(const bgp_handle* h);
+
+/* Upper bound on work items processed concurrently (one workspace slot each).  0 restores the default (one per SM). */
+int bgp_set_max_slots(bgp_handle* h, int max_slots);
+/* Bytes of library workspace one dense / sparse work item needs at the given shape. */
+size_t bgp_dense_slot_bytes(int N, int D);
+
+/* Pinned host memory for the `_host` entry points (plain malloc'ed buffers work too, just slower). */
+int bgp_host_alloc(void** p, size_t bytes);
+int bgp_host_free(void* p);
+
+/* Dense AssignGP bound + gradient.  Replaces AssignGP.maximum_log_likelihood_objective (assigngp_dense.py:151-199)
+ * and the TF autodiff gradient that gpflow.optimizers.Scipy requests (FitBranchingModel.py:127-132).
+ *
+ *   t[N]                 pseudotime of each cell
+ *   Y[nY][N][D]          expression; item i uses Y[item_gene[i]]
+ *   b[count]             candidate branching point of item i (kernel and trunk/branch split t <= b)
+ *   prior                BGP: phiPrior[N][2];  MBGP: prior[N][3]
+ *   hyp[count][3]        lengthscale, kernel variance, likelihood variance (constrained values)
+ *   logPhi[count][N][3N] variational logits
+ *   KConst[3N][3N]       optional fixed covariance (AssignGP(KConst=...), assigngp_dense.py:156-158), else NULL
+ *   kl_weight            1 for BGP, D for MBGP multi=False (MBGP/assigngp.py:637)
+ *   want_grad            0: bound only
+ * outputs
+ *   elbo[count]          the bound (without hyper-priors)
+ *   grad_hyp[count][4]   d elbo / d (lengthscale, kernel variance, likelihood variance, b)   (may be NULL if !want_grad)
+ *   grad_logPhi[count][N][3N]                                                                 (may be NULL if !want_grad)
+ *   status[count]
+ */
+int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
+                        const int* item_gene, const double* b, const double* prior, const double* hyp, int kernel_kind,
+                        int model, double kl_weight, const double* logPhi, const double* KConst, int want_grad,
+                        double* elbo, double* grad_hyp, double* grad_logPhi, int* status, void* cuda_stream);
+
+/* Same, HOST pointers; copies in/out inside the call and synchronises before returning. */
+int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
+                             const int* item_gene, const double* b, const double* prior, const double* hyp,
+                             int kernel_kind, int model, double kl_weight, const double* logPhi, const double* KConst,
+                             int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status);
+
+/* AssignGP.GetPhi (assigngp_dense.py:130-140): softmax rows of logPhi gathered at the cell's own 3 columns -> Phi[count][N][3].
+ * HOST pointers. */
+int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi);
+
+/* ---- test hooks (used by tests/ only) ------------------------------------------------------------------------
+ * Stop the dense pipeline after phase `phase` (1 chol K, 2 P, 3 chol P, 4 solve, 5 trtri, 6 lauum, 7 trmm, 8 post,
+ * 9 adjoint; 0 = run everything) and read back workspace matrices / vectors of a slot of the last wave. */
+int bgp_debug_set_stop_phase(bgp_handle* h, int phase);
+int bgp_debug_padded_size(int N);
+/* which: 0 LC (chol K), 1 RX (P / R / R^-1), 2 PB (Pbar), 3 LB (Lbar / Ktilde); out_host[Mp*Mp] row-major */
+int bgp_debug_dense_matrix(bgp_handle* h, int slot, int which, int symmetric, double* out_host);
+/* which: 0 A, 1 Delta, 2 v, 3 z, 4 c, 5 q, 6 vbar, 7 delta, 8 Abar; out_host[len] (len = Mp or D*Mp) */
+int bgp_debug_dense_vector(bgp_handle* h, int slot, int which, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRANCHEDGP_B200_H */
