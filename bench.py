@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the BranchedGP hot path on B200: ELBO + gradient evaluations per second (gene x branch-point work
+items) for the dense AssignGP bound at N = 1000 cells (BASELINE.json configs[1], "C2").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A step is one pass of the hot path (bound + full gradient) over one batch of
+`--items` distinct work items of the C2 grid (512 genes x 20 branching points); every rank owns its own batch (weak
+scaling, no data-path collective) and the per-item ELBOs / hyper-gradients are gathered over NCCL at the end of a
+step.  See DESIGN.md section "Measurement" for how each field is produced.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GENES, N_B = 512, 20
+METRIC = "elbo_grad_evals_per_s"
+UNIT = "items/s"
+
+
+def c2_grid():
+    return np.concatenate([np.linspace(0.05, 0.95, N_B - 1), [1.1]])   # last entry = "no branching" null (VBHelperFunctions.py:13)
+
+
+def phase_flops(N):
+    """Algorithmic fp64 flops per work item of each GEMM-shaped kernel, M = 3N."""
+    M3 = float(3 * N) ** 3
+    return {"chol_K": M3 / 3, "syrk_P": M3 / 3, "chol_P": M3 / 3, "trtri": M3 / 3, "lauum": M3 / 3, "trmm": 2 * M3 / 3,
+            "adjoint": 2 * M3 / 3}
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for k, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def fp64_peak():
+    """FP64 roofline denominator.  MEASURED_PEAKS.json (driver-written) carries only HBM and bf16, so the fp64 figure is
+    this repo's own measurement on the same pool (tools/microbench -> profiles/r01_fp64_peak.json, r01_lib_peaks.json)."""
+    out = {"dmma_tflops": 37.14, "cublas_dgemm_tflops": 35.44, "source": "profiles/r01_fp64_peak.json (DMMA m8n8k4 issue rate), "
+           "profiles/r01_lib_peaks.json (cuBLAS DGEMM 8192^3); MEASURED_PEAKS.json has no fp64 entry"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")) as f:
+            out["dmma_tflops"] = float(json.load(f)["dmma_tflops_bps8"])
+        with open(os.path.join(ROOT, "profiles", "r01_lib_peaks.json")) as f:
+            out["cublas_dgemm_tflops"] = float(json.load(f)["dgemm_8192_tflops"])
+    except Exception:
+        pass
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def synth_host(N, seed=0):
+    """Item-independent inputs of SURVEY.md 8d: pseudotime, labels, FitModel's prior / initial phi, Y for all genes."""
+    from branchedgp_b200.FitBranchingModel import GetInitialConditionsAndPrior
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0.0, 1.0, N))
+    labels = np.where(t < 0.3, 1, rng.integers(2, 4, N))
+    phi0, prior = GetInitialConditionsAndPrior(labels, 0.8, True)
+    bg = rng.uniform(0.1, 0.9, N_GENES)
+    ag = rng.uniform(0.5, 3.0, N_GENES)
+    sign = np.where(labels == 3, -1.0, 1.0)
+    Y = sign[None, :] * ag[:, None] * np.maximum(t[None, :] - bg[:, None], 0.0) + 0.3 * rng.standard_normal((N_GENES, N))
+    Y -= Y.mean(axis=1, keepdims=True)
+    hyp = np.stack([rng.uniform(0.5, 3.0, N_GENES * N_B), rng.uniform(1.0, 6.0, N_GENES * N_B),
+                    rng.uniform(0.05, 1.0, N_GENES * N_B)], axis=1)
+    return dict(t=t, labels=labels, phi0=phi0, prior=prior, Y=Y[:, :, None].copy(), hyp=hyp)
+
+
+def item_arrays(first, n):
+    """(gene index, branching point) of n consecutive items of the C2 grid starting at `first` (wrapping)."""
+    idx = (first + np.arange(n)) % (N_GENES * N_B)
+    grid = c2_grid()
+    return idx, (idx // N_B).astype(np.int32), grid[idx % N_B]
+
+
+def init_logphi_device(torch, dev, N, phi0, t, b_items, seed):
+    """InitialiseVariationalPhi (assigngp_dense.py:92-128) for every item, plus 0.1 N(0,1) so items are distinct."""
+    n = len(b_items)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lp = torch.full((n, N, 3 * N), -9.0, dtype=torch.float64, device=dev)
+    eps = 1e-9
+    tt = torch.as_tensor(t, device=dev)
+    bb = torch.as_tensor(b_items, device=dev)
+    act = tt[None, :] > bb[:, None]                                  # [n, N]
+    p0 = torch.as_tensor(phi0, device=dev)
+    branch = torch.log(torch.stack([torch.full((N,), eps, dtype=torch.float64, device=dev), p0[:, 0] - eps, p0[:, 1] - eps], 1))
+    trunk = torch.log(torch.tensor([1 - 2 * eps, eps, eps], dtype=torch.float64, device=dev))
+    blk = torch.where(act[:, :, None], branch[None], trunk[None, None, :])   # [n, N, 3]
+    ar = torch.arange(N, device=dev)
+    for f in range(3):
+        lp[:, ar, 3 * ar + f] = blk[:, :, f]
+    lp += 0.1 * torch.randn(lp.shape, generator=g, dtype=torch.float64, device=dev)
+    return lp
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from branchedgp_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, ips = args.cells, args.items
+    eng = _lib.Engine(local)
+    H = synth_host(N)
+    d = {k: torch.as_tensor(H[k], device=dev).contiguous() for k in ("t", "prior", "Y")}
+    hyp_all = torch.as_tensor(H["hyp"], device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # this rank's batch of items; logPhi (ips x 24 MB) is far larger than the 126 MB L2, so no flush is needed
+    first = rank * ips
+    _, gene0, b0 = item_arrays(first, ips)
+    logPhi = init_logphi_device(torch, dev, N, H["phi0"], H["t"], b0, seed=1234 + rank)
+    grad = torch.empty_like(logPhi)
+    elbo = torch.empty(ips, dtype=torch.float64, device=dev)
+    gh = torch.zeros(ips, 4, dtype=torch.float64, device=dev)
+    status = torch.zeros(ips, dtype=torch.int32, device=dev)
+    res_local = torch.empty(ips, 5, dtype=torch.float64, device=dev)
+    res_all = torch.empty(world * ips, 5, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step(k):
+        idx, gene, bb = item_arrays(first + k * world * ips, ips)
+        gene_d = torch.as_tensor(gene, device=dev)
+        b_d = torch.as_tensor(bb, device=dev)
+        hyp_d = hyp_all[torch.as_tensor(idx, device=dev)].contiguous()
+        eng.dense_elbo_grad_device(ips, N, 1, d["t"].data_ptr(), d["Y"].data_ptr(), N_GENES, gene_d.data_ptr(), b_d.data_ptr(),
+                                   d["prior"].data_ptr(), hyp_d.data_ptr(), logPhi.data_ptr(), elbo.data_ptr(), gh.data_ptr(),
+                                   grad.data_ptr(), status.data_ptr(), stream=stream)
+        if world > 1:   # the only collective of the path: gather per-item ELBO + hyper-gradient
+            res_local[:, 0] = elbo
+            res_local[:, 1:] = gh
+            dist.all_gather_into_tensor(res_all, res_local)
+        return gene_d, b_d, hyp_d   # keep alive until the stream has consumed them
+
+    keep = []
+    for k in range(args.warmup):
+        keep.append(step(k))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.profile_enable(True)
+    eng.profile_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(args.steps):
+        keep.append(step(args.warmup + k))
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    phase_ms, launches = eng.profile_read()
+    eng.profile_enable(False)
+    bad = int((status != 0).sum().item())
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = world * ips * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's own launches)
+    fl = phase_flops(N)
+    dom = max(fl, key=lambda k: phase_ms[k])
+    slots = min(ips, eng.sm_count)                       # one workspace slot per SM: a launch covers `slots` items
+    waves_per_step = math.ceil(ips / slots)
+    launch_ms = phase_ms[dom] / (args.steps * waves_per_step)
+    items_per_launch = ips / waves_per_step
+    achieved = fl[dom] * items_per_launch / (launch_ms * 1e-3) / 1e12
+    pk = fp64_peak()
+    gemm_ms = sum(phase_ms[k] for k in fl)
+    total_flops = sum(fl.values()) * ips * args.steps
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 3), "peak": pk["dmma_tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["dmma_tflops"], 4), "traffic": None,
+                "launch_ms": round(launch_ms, 3), "items_per_launch": items_per_launch,
+                "flops_per_item": fl[dom], "peak_source": pk["source"], "cublas_dgemm_tflops": pk["cublas_dgemm_tflops"],
+                "whole_step_tflops": round(total_flops / (ms * 1e-3) / 1e12, 3),
+                "whole_step_frac": round(total_flops / (ms * 1e-3) / 1e12 / pk["dmma_tflops"], 4),
+                "phase_ms_per_step": {k: round(v / args.steps, 3) for k, v in phase_ms.items()},
+                "gemm_kernels_share_of_step": round(gemm_ms / ms, 4)}
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_items, ips)
+        h_lp = torch.empty((ne, N, 3 * N), dtype=torch.float64).pin_memory()
+        h_lp.copy_(logPhi[:ne])
+        idx, gene, bb = item_arrays(first, ne)
+        hyp_h = H["hyp"][idx]
+        del grad, logPhi
+        torch.cuda.empty_cache()
+        import ctypes
+        gptr = ctypes.c_void_p()
+        nbytes = ne * N * 3 * N * 8
+        assert eng._lib.bgp_host_alloc(ctypes.byref(gptr), nbytes) == 0
+        g_host = np.ctypeslib.as_array(ctypes.cast(gptr, ctypes.POINTER(ctypes.c_double)), shape=(ne, N, 3 * N))
+        out = None
+        reps = max(1, min(args.steps, 3))
+        tbest = []
+        for r in range(1 + reps):   # first repetition is a warm-up
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = eng.dense_elbo_grad(H["t"], H["Y"], gene, bb, H["prior"], hyp_h, h_lp.numpy(), grad_out=g_host)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if r > 0:
+                tbest.append(dt)
+        tt = torch.tensor([sum(tbest) / len(tbest)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * ne / float(tt.item()), 3), "unit": UNIT, "items_per_step": ne,
+               "h2d_bytes_per_step": int(nbytes + ne * 40), "d2h_bytes_per_step": int(nbytes + ne * 44),
+               "api": "bgp_dense_elbo_grad_host (ctypes, pinned host buffers)", "timer": "host wall clock around the call, max over ranks",
+               "elbo_checksum": float(out["elbo"].sum())}
+        eng._lib.bgp_host_free(gptr)
+
+    line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: BGP dense AssignGP bound+grad, N={N} cells (M=3N={3 * N}), grid of {N_GENES} genes x {N_B} "
+                                   f"branching points; one step = {ips} distinct work items per GPU",
+                       "items_per_step_per_gpu": ips, "cells": N, "D": 1, "kernel": "Matern32",
+                       "l2": "inputs larger than L2 (logPhi+grad = %.1f GB per step), no flush" % (2 * ips * N * 3 * N * 8 / 1e9),
+                       "parallelism": f"items sharded over {world} GPU(s), NCCL all_gather of [items,5] results per step"},
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "status_nonzero": bad}
+    if rank == 0 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(N, H, kind="port", budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _host_problem(N, H, k):
+    """Dense numpy inputs of item k for the CPU oracle."""
+    from oracle import host_ref
+    idx, gene, bb = item_arrays(k, 1)
+    b = float(bb[0])
+    X, _ = host_ref.function_index_list(H["t"])
+    pZ = host_ref.prior_with_trunk_bgp(host_ref.expand_prior_bgp(H["prior"]), b, H["t"])
+    rng = np.random.default_rng(1000 + k)
+    lp = host_ref.init_logphi_bgp(H["phi0"], H["t"], b) + 0.1 * rng.standard_normal((N, 3 * N))
+    return lp, H["Y"][gene[0]], X, pZ, b, H["hyp"][idx[0]]
+
+
+def cpu_baseline(N, H, kind, budget_s=20.0, impl="numpy"):
+    """Time the CPU oracle (test infrastructure; the one sanctioned use outside tests) on a bounded sample of the workload."""
+    import torch
+    from oracle import bgp_numpy, bgp_torch
+    fn = bgp_numpy.dense_value_and_grad if impl == "numpy" else bgp_torch.dense_value_and_grad
+    times, k = [], 0
+    t_start = time.perf_counter()
+    while True:
+        lp, Y, X, pZ, b, hyp = _host_problem(N, H, k)
+        t0 = time.perf_counter()
+        fn(lp, Y, X, pZ, b, hyp[0], hyp[1], hyp[2])
+        times.append(time.perf_counter() - t0)
+        k += 1
+        if k >= 2 and time.perf_counter() - t_start > budget_s:
+            break
+    per = float(np.mean(times[1:])) if len(times) > 1 else times[0]
+    return {"value": round(1.0 / per, 4), "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": kind,
+            "sample": f"{len(times) - 1} timed + 1 warm-up work items of the same workload (N={N}), "
+                      f"oracle.{'bgp_numpy (LAPACK + hand adjoint)' if impl == 'numpy' else 'bgp_torch (op-for-op restatement + autograd)'}",
+            "s_per_item": round(per, 4)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own formulation of the path (op-for-op float64 restatement of the TF/GPflow graph with
+    reverse-mode autodiff, oracle/bgp_torch.py) on the host cores.  TensorFlow/GPflow cannot be installed here (no wheels in
+    /opt/wheelhouse, no network), so oracle/_ref does not exist and kind = "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    N = args.cells
+    H = synth_host(N)
+    from oracle import bgp_torch
+    k = 0
+    times = []
+    per_step = max(1, args.ref_items)
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for _ in range(per_step):
+            lp, Y, X, pZ, b, hyp = _host_problem(N, H, k)
+            bgp_torch.dense_value_and_grad(lp, Y, X, pZ, b, hyp[0], hyp[1], hyp[2])
+            k += 1
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    value = per_step * args.steps / tot
+    cb = {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+          "sample": f"{per_step} work item(s) per step of the same workload (N={N}); oracle.bgp_torch = restatement of the TF 2.4 / "
+                    "GPflow 2.1.2 graph + autodiff (reference not installable here)"}
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: BGP dense AssignGP bound+grad, N={N} cells (M=3N={3 * N}), grid of {N_GENES} genes x {N_B} "
+                                   f"branching points; one step = {per_step} work item(s) on the host CPU"},
+            "cpu_baseline": cb, "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=1000, help="N (C2 = 1000)")
+    ap.add_argument("--items", type=int, default=296, help="work items per step per GPU")
+    ap.add_argument("--e2e-items", type=int, default=148)
+    ap.add_argument("--ref-items", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,9 @@ SIGNATURES = {
                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_get_phi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bgp_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
+    "bgp_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "bgp_debug_set_stop_phase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bgp_debug_padded_size": (ctypes.c_int, [ctypes.c_int]),
     "bgp_debug_dense_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -127,7 +130,7 @@ class Engine:
 
     # ------------------------------------------------------------------ dense bound
     def dense_elbo_grad(self, t, Y, item_gene, b, prior, hyp, logPhi, kernel=KERNEL_MATERN32, model=MODEL_BGP,
-                        kl_weight=1.0, KConst=None, want_grad=True, check=True):
+                        kl_weight=1.0, KConst=None, want_grad=True, check=True, grad_out=None):
         """Host-array entry: Y [nY,N,D], item_gene [count], b [count], hyp [count,3], logPhi [count,N,3N]."""
         t = _f64(t)
         Y = _f64(Y)
@@ -149,7 +152,10 @@ class Engine:
         elbo = np.empty(count)
         status = np.empty(count, dtype=np.int32)
         grad_hyp = np.zeros((count, 4)) if want_grad else None
-        grad_logPhi = np.empty((count, N, 3 * N)) if want_grad else None
+        grad_logPhi = None
+        if want_grad:
+            grad_logPhi = grad_out if grad_out is not None else np.empty((count, N, 3 * N))
+            assert grad_logPhi.shape == (count, N, 3 * N) and grad_logPhi.dtype == np.float64 and grad_logPhi.flags.c_contiguous
         rc = self._lib.bgp_dense_elbo_grad_host(self._h, count, N, D, _ptr(t), _ptr(Y), nY, _ptr(item_gene), _ptr(b),
                                                 _ptr(prior), _ptr(hyp), int(kernel), int(model), float(kl_weight),
                                                 _ptr(logPhi), _ptr(KConst), int(bool(want_grad)), _ptr(elbo),
@@ -179,6 +185,23 @@ class Engine:
         out = np.empty((count, N, 3))
         self._check(self._lib.bgp_get_phi_host(self._h, count, N, _ptr(logPhi), _ptr(out)), "bgp_get_phi_host")
         return out
+
+    # ------------------------------------------------------------------ per-kernel timing
+    PHASES = ("phi_forward", "prep", "chol_K", "syrk_P", "chol_P", "solve", "trtri", "lauum", "trmm", "post", "adjoint",
+              "phi_backward")
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.bgp_profile_enable(self._h, int(bool(on))), "bgp_profile_enable")
+
+    def profile_reset(self):
+        self._check(self._lib.bgp_profile_reset(self._h), "bgp_profile_reset")
+
+    def profile_read(self):
+        """(dict phase -> accumulated ms since the last reset, kernel launches since the last reset); waits for the GPU."""
+        ms = np.zeros(len(self.PHASES))
+        n = ctypes.c_longlong(0)
+        self._check(self._lib.bgp_profile_read(self._h, _ptr(ms), ctypes.byref(n)), "bgp_profile_read")
+        return dict(zip(self.PHASES, ms.tolist())), int(n.value)
 
     # ------------------------------------------------------------------ test hooks
     def debug_set_stop_phase(self, phase):

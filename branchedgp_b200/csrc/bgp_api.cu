@@ -25,7 +25,27 @@ struct bgp_handle {
     DenseParams lastP;
     int last_slots = 0;
     bool kernels_ready = false;
+    // optional per-kernel timing (bench.py): events recorded around every launch of a call
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_marks;   // (phase id, index into ev_pool of the event recorded AFTER the launch)
+    int ev_used = 0;
+    double prof_ms[BGP_NPHASES] = {0};
+    long long launches = 0;
 };
+
+static void prof_mark(bgp_handle* h, int phase, cudaStream_t st) {
+    if (phase >= 0) h->launches++;
+    if (!h->profiling) return;
+    if (h->ev_used == (int)h->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    cudaEventRecord(h->ev_pool[h->ev_used], st);
+    h->ev_marks.push_back({phase, h->ev_used});
+    h->ev_used++;
+}
 
 static int fail(bgp_handle* h, int code, const char* fmt, ...) {
     if (h) {
@@ -101,6 +121,7 @@ int bgp_create(int device, bgp_handle** out) {
 int bgp_destroy(bgp_handle* h) {
     if (!h) return BGP_OK;
     cudaSetDevice(h->device);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
     delete h;
@@ -190,10 +211,22 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
         const int n = (count - item0 < slots) ? (count - item0) : slots;
         P.item0 = item0;
         F.item0 = item0;
+        const int last = h->stop_phase > 0 ? h->stop_phase : 99;
+        prof_mark(h, -1, st);
         phi_launch_forward(F, n, st);
+        prof_mark(h, 0, st);
         dense_launch_prep(P, F.Apart, F.vpart, F.klpart, Y, item_gene, n, st);
-        dense_launch_pipeline(P, n, want_grad, h->stop_phase, st);
-        if (want_grad && (h->stop_phase == 0 || h->stop_phase >= 9)) phi_launch_backward(F, n, st);
+        prof_mark(h, 1, st);
+        for (int phase = 1; phase <= 9 && phase <= last; ++phase) {
+            const bool grad_phase = (phase == 5 || phase == 6 || phase == 7 || phase == 9);
+            if (grad_phase && !want_grad) continue;
+            dense_launch_phase(P, n, phase, st);
+            prof_mark(h, phase + 1, st);
+        }
+        if (want_grad && last >= 9) {
+            phi_launch_backward(F, n, st);
+            prof_mark(h, 11, st);
+        }
         CU(cudaGetLastError());
         h->last_slots = n;
     }
@@ -287,6 +320,40 @@ int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, doub
         CU(cudaMemcpyAsync(phi + (size_t)i * N * 3, s + align_up(per_item, 256), (size_t)N * 3 * 8, cudaMemcpyDeviceToHost, 0));
         CU(cudaStreamSynchronize(0));
     }
+    return BGP_OK;
+}
+
+// ---- per-kernel timing ------------------------------------------------------------------------------------------
+int bgp_profile_enable(bgp_handle* h, int on) {
+    if (!h) return BGP_ERR_ARG;
+    h->profiling = on != 0;
+    return BGP_OK;
+}
+int bgp_profile_reset(bgp_handle* h) {
+    if (!h) return BGP_ERR_ARG;
+    for (int i = 0; i < BGP_NPHASES; ++i) h->prof_ms[i] = 0.0;
+    h->launches = 0;
+    h->ev_marks.clear();
+    h->ev_used = 0;
+    return BGP_OK;
+}
+int bgp_profile_read(bgp_handle* h, double* ms_out, long long* launches) {
+    if (!h) return BGP_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    if (!h->ev_marks.empty()) {
+        CU(cudaEventSynchronize(h->ev_pool[h->ev_marks.back().second]));
+        for (size_t i = 1; i < h->ev_marks.size(); ++i) {
+            const int phase = h->ev_marks[i].first;
+            if (phase < 0) continue;   // start-of-wave marker
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, h->ev_pool[h->ev_marks[i - 1].second], h->ev_pool[h->ev_marks[i].second]));
+            h->prof_ms[phase] += ms;
+        }
+        h->ev_marks.clear();
+        h->ev_used = 0;
+    }
+    if (ms_out) for (int i = 0; i < BGP_NPHASES; ++i) ms_out[i] = h->prof_ms[i];
+    if (launches) *launches = h->launches;
     return BGP_OK;
 }
 

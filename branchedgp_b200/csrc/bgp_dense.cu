@@ -710,20 +710,20 @@ void dense_launch_prep(const DenseParams& P, const double* Apart, const double* 
     k_prep<<<nitems, NTHREADS, 0, st>>>(P, Q);
 }
 
-// stop_phase > 0 stops after that phase (test hook); want_grad = 0 computes the bound only.
-void dense_launch_pipeline(const DenseParams& P, int nitems, int want_grad, int stop_phase, cudaStream_t st) {
-    const int last = stop_phase > 0 ? stop_phase : 99;
-    if (last >= 1) k_chol<0><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
-    if (last >= 2) k_syrk<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
-    if (last >= 3) k_chol<1><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
-    if (last >= 4) k_solve<<<nitems, NTHREADS, 0, st>>>(P);
-    if (want_grad) {
-        if (last >= 5) k_trtri<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
-        if (last >= 6) k_lauum<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
-        if (last >= 7) k_trmm<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
+// phase: 1 chol K, 2 P, 3 chol P, 4 solve, 5 trtri, 6 lauum, 7 trmm, 8 post, 9 adjoint
+void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_t st) {
+    switch (phase) {
+        case 1: k_chol<0><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 2: k_syrk<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 3: k_chol<1><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 4: k_solve<<<nitems, NTHREADS, 0, st>>>(P); break;
+        case 5: k_trtri<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 6: k_lauum<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 7: k_trmm<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 8: k_post<<<nitems, NTHREADS, 0, st>>>(P); break;
+        case 9: k_adj<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        default: break;
     }
-    if (last >= 8) k_post<<<nitems, NTHREADS, 0, st>>>(P);
-    if (want_grad && last >= 9) k_adj<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P);
 }
 
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st) {

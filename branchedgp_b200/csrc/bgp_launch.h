@@ -7,7 +7,7 @@ namespace bgp {
 cudaError_t dense_init_kernels();
 void dense_launch_prep(const DenseParams& P, const double* Apart, const double* vpart, const double* klpart, const double* Y,
                        const int* item_gene, int nitems, cudaStream_t st);
-void dense_launch_pipeline(const DenseParams& P, int nitems, int want_grad, int stop_phase, cudaStream_t st);
+void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_t st);
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st);
 void phi_launch_gather(const double* logPhi, double* phi, int count, int N, cudaStream_t st);
 }  // namespace bgp

@@ -88,6 +88,15 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
  * HOST pointers. */
 int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi);
 
+/* Per-kernel device timing (CUDA events recorded on the caller's stream around every launch).  Phase ids:
+ * 0 phi forward, 1 prep, 2 chol K, 3 P = L^T D L + I, 4 chol P, 5 solves, 6 trtri, 7 lauum, 8 trmm, 9 post, 10 adjoint,
+ * 11 phi backward.  bgp_profile_read waits for the recorded events, accumulates milliseconds per phase since the last
+ * reset into ms_out[BGP_NPHASES] and returns the number of kernel launches made since the last reset. */
+#define BGP_NPHASES 12
+int bgp_profile_enable(bgp_handle* h, int on);
+int bgp_profile_reset(bgp_handle* h);
+int bgp_profile_read(bgp_handle* h, double* ms_out, long long* launches);
+
 /* ---- test hooks (used by tests/ only) ------------------------------------------------------------------------
  * Stop the dense pipeline after phase `phase` (1 chol K, 2 P, 3 chol P, 4 solve, 5 trtri, 6 lauum, 7 trmm, 8 post,
  * 9 adjoint; 0 = run everything) and read back workspace matrices / vectors of a slot of the last wave. */

@@ -1,0 +1,90 @@
+"""CPU suite: host-side mirror of the reference API (no GPU calls)."""
+import numpy as np
+import pytest
+
+from branchedgp_b200 import BranchingTree as bt
+from branchedgp_b200 import FitBranchingModel, VBHelperFunctions, pZ_construction_singleBP
+from branchedgp_b200 import branch_kernParamGPflow as bk
+from branchedgp_b200 import gpflow_shim as gpflow
+from oracle import bgp_numpy, host_ref
+
+
+def test_initial_conditions_and_prior_match_loop_restatement():
+    rng = np.random.default_rng(1)
+    labels = rng.integers(1, 4, 57).astype(float)
+    for inf in (True, False):
+        a, b = FitBranchingModel.GetInitialConditionsAndPrior(labels, 0.8, inf)
+        c, d = host_ref.initial_conditions_and_prior(labels, 0.8, inf)
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+def test_function_index_list_is_cell_major():
+    t = np.linspace(0, 1, 7)
+    X, idx, XS = VBHelperFunctions.GetFunctionIndexListGeneral(t)
+    X2, idx2 = host_ref.function_index_list(t)
+    assert np.array_equal(X, X2) and idx == idx2
+    assert XS.shape == (7, 2) and set(XS[:, 1]) <= {1.0, 2.0, 3.0}
+
+
+def test_pZ_construction_matches_reference_rules():
+    """testing/test_pZ_construct.py: trunk rows are [1, eps, eps]; branch rows keep the prior in columns 1, 2."""
+    t = np.linspace(0, 1, 9)
+    prior = np.tile([0.3, 0.7], (9, 1))
+    e = pZ_construction_singleBP.expand_pZ0Zeros(prior)
+    assert np.array_equal(e, host_ref.expand_prior_bgp(prior))
+    p = pZ_construction_singleBP.expand_pZ0PureNumpyZeros(e, np.ones((1, 1)) * 0.5, t)
+    assert np.array_equal(p, host_ref.prior_with_trunk_bgp(e, 0.5, t))
+    for i in range(9):
+        blk = p[i, 3 * i:3 * i + 3]
+        if t[i] <= 0.5:
+            assert np.allclose(blk, [1, 1e-6, 1e-6], atol=1e-12)
+        else:
+            assert np.allclose(blk, [1e-6, 0.3, 0.7], atol=1e-12)
+    with pytest.raises(AssertionError):
+        pZ_construction_singleBP.expand_pZ0Zeros(np.ones((3, 3)) / 3)
+
+
+def test_branching_evidence_and_posterior():
+    ll = np.array([-10.0, -3.0, -7.0, -20.0])
+    B = [0.1, 0.4, 0.7, 1.1]
+    ev = VBHelperFunctions.CalculateBranchingEvidence({"loglik": ll}, B)
+    w = np.exp(ll[:-1] - ll[:-1].max())
+    assert np.allclose(ev["posteriorBranching"], w / w.sum())
+    assert np.isclose(ev["logBayesFactor"], np.log(np.exp(ll[:-1]).sum()) - ll[-1] - np.log(3))
+    with pytest.raises(NameError):
+        VBHelperFunctions.CalculateBranchingEvidence({"loglik": ll}, B[:-1])
+    post = FitBranchingModel.GetPosteriorB(ll, B)
+    assert post["Bmode"] == 0.4 and post["idx_mode"] == 1
+    assert list(post["BgridSearch_sort"]) == B
+
+
+def test_tree_tensor_for_one_branch_point():
+    tree = bt.BinaryBranchingTree(0, 1)
+    tree.add(None, 1, np.ones((1, 1)) * 0.3)
+    fm, _ = tree.GetFunctionBranchTensor()
+    assert fm.shape == (3, 3, 1)
+    assert np.all(fm[~np.eye(3, dtype=bool), 0] == 1) and np.all(np.isnan(np.diag(fm[:, :, 0])))
+
+
+def test_parameter_transforms_and_kernel_container():
+    p = gpflow.Parameter(2.5, transform=gpflow.positive(1e-6))
+    assert np.isclose(float(p.numpy()), 2.5)
+    u = p.unconstrained_variable
+    h = 1e-6
+    num = (gpflow.positive(1e-6).forward(u + h) - gpflow.positive(1e-6).forward(u - h)) / (2 * h)
+    assert np.isclose(num, p.transform.dforward(u), rtol=1e-6)
+    s = gpflow.Sigmoid()
+    assert np.isclose(s.forward(s.inverse(0.3)), 0.3)
+    tree = bt.BinaryBranchingTree(0, 1)
+    tree.add(None, 1, np.ones((1, 1)) * 0.3)
+    fm, _ = tree.GetFunctionBranchTensor()
+    kb = bk.BranchKernelParam(gpflow.kernels.Matern32(1), fm, b=np.ones((1, 1)) * 0.4) + gpflow.kernels.White(1)
+    kb.kernels[1].variance.assign(1e-6)
+    gpflow.set_trainable(kb.kernels[1].variance, False)
+    assert kb.kernels[0].name == "branch_kernel_param" and not kb.kernels[1].variance.trainable
+    kb.kernels[0].kern.lengthscales.assign(1.7)
+    X, _, _ = VBHelperFunctions.GetFunctionIndexListGeneral(np.linspace(0, 1, 5))
+    K = kb.kernels[0].K(X)
+    assert np.allclose(K, bgp_numpy.branch_K(X, X, 0.4, 1.7, 1.0, 0), rtol=1e-13)
+    n = gpflow.Normal(2.0, 1.0)
+    assert np.isclose(n.log_prob(2.0), -0.5 * np.log(2 * np.pi))
