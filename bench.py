@@ -28,6 +28,11 @@ METRIC = "elbo_grad_evals_per_s"
 UNIT = "items/s"
 
 
+def workload_name(N):
+    return (f"C2: BGP dense AssignGP bound+grad, N={N} cells (M=3N={3 * N}), grid of {N_GENES} genes x {N_B} branching points; "
+            "a step = one batch of distinct (gene, branching point) work items")
+
+
 def c2_grid():
     return np.concatenate([np.linspace(0.05, 0.95, N_B - 1), [1.1]])   # last entry = "no branching" null (VBHelperFunctions.py:13)
 
@@ -266,8 +271,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: BGP dense AssignGP bound+grad, N={N} cells (M=3N={3 * N}), grid of {N_GENES} genes x {N_B} "
-                                   f"branching points; one step = {ips} distinct work items per GPU",
+            "config": {"workload": workload_name(N),
                        "items_per_step_per_gpu": ips, "cells": N, "D": 1, "kernel": "Matern32",
                        "l2": "inputs larger than L2 (logPhi+grad = %.1f GB per step), no flush" % (2 * ips * N * 3 * N * 8 / 1e9),
                        "parallelism": f"items sharded over {world} GPU(s), NCCL all_gather of [items,5] results per step"},
@@ -345,8 +349,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: BGP dense AssignGP bound+grad, N={N} cells (M=3N={3 * N}), grid of {N_GENES} genes x {N_B} "
-                                   f"branching points; one step = {per_step} work item(s) on the host CPU"},
+            "config": {"workload": workload_name(N), "items_per_step": per_step},
             "cpu_baseline": cb, "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
