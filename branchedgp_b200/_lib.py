@@ -42,6 +42,16 @@ SIGNATURES = {
                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_sparse_elbo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_sparse_elbo_grad_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_get_phi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bgp_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
@@ -175,6 +185,44 @@ class Engine:
                                            float(kl_weight), logPhi, KConst or None, int(bool(want_grad)), elbo,
                                            grad_hyp or None, grad_logPhi or None, status, stream or None)
         self._check(rc, "bgp_dense_elbo_grad")
+
+    # ------------------------------------------------------------------ inducing-point bounds
+    def sparse_elbo_grad(self, t, Z, Y, item_gene, b, prior, hyp, logPhi, kernel=KERNEL_MATERN32, model=MODEL_BGP, multi=False,
+                         want_grad=True, check=True, grad_out=None):
+        """Host-array entry.  Y [nY,N,Dtot]; b [count] (multi=False) or [count,Dtot] (multi=True); Z [Mz,2]."""
+        t = _f64(t)
+        Z = _f64(Z)
+        Y = _f64(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        nY, N, Dtot = Y.shape
+        Mz = Z.shape[0]
+        item_gene = np.ascontiguousarray(item_gene, dtype=np.int32)
+        count = item_gene.size
+        SD = Dtot if multi else 1
+        b = _f64(b).reshape(count, SD)
+        hyp = _f64(hyp).reshape(count, 3)
+        prior = _f64(prior)
+        logPhi = _f64(logPhi).reshape(count, N, 3 * N)
+        assert t.shape == (N,) and Z.shape == (Mz, 2)
+        assert prior.shape == (N, 3 if model == MODEL_MBGP else 2)
+        elbo = np.empty(count)
+        status = np.empty(count, dtype=np.int32)
+        grad_hyp = np.zeros((count, 3)) if want_grad else None
+        grad_b = np.zeros((count, SD)) if want_grad else None
+        grad_logPhi = None
+        if want_grad:
+            grad_logPhi = grad_out if grad_out is not None else np.empty((count, N, 3 * N))
+        rc = self._lib.bgp_sparse_elbo_grad_host(self._h, count, N, Dtot, Mz, _ptr(t), _ptr(Z), _ptr(Y), nY, _ptr(item_gene), _ptr(b),
+                                                 _ptr(prior), _ptr(hyp), int(kernel), int(model), int(bool(multi)), _ptr(logPhi),
+                                                 int(bool(want_grad)), _ptr(elbo), _ptr(grad_hyp), _ptr(grad_b), _ptr(grad_logPhi),
+                                                 _ptr(status))
+        self._check(rc, "bgp_sparse_elbo_grad_host")
+        if check and (status != 0).any():
+            i = int(np.flatnonzero(status)[0])
+            raise CholeskyError(f"Cholesky decomposition was not successful for work item {i} (status {int(status[i])}): "
+                                "the input might not be valid")
+        return dict(elbo=elbo, grad_hyp=grad_hyp, grad_b=grad_b, grad_logPhi=grad_logPhi, status=status)
 
     def get_phi(self, logPhi):
         logPhi = _f64(logPhi)

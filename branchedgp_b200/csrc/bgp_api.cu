@@ -114,6 +114,7 @@ int bgp_create(int device, bgp_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) return fail(h, BGP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CU(dense_init_kernels());
+    CU(sparse_init_kernels());
     h->kernels_ready = true;
     return BGP_OK;
 }
@@ -199,6 +200,7 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
     PhiParams F;
     memset(&F, 0, sizeof(F));
     F.N = N; F.M = d.M; F.Mp = d.Mp; F.D = D; F.nch = d.nch; F.model = model; F.kl_weight = kl_weight;
+    F.SD = 1; F.Dtot = D;
     F.logPhi = logPhi; F.t = t; F.prior = prior; F.bv = b; F.Y = Y; F.item_gene = item_gene;
     F.lse = (double*)(base + SL.lse); F.Apart = (double*)(base + SL.Apart); F.vpart = (double*)(base + SL.vpart);
     F.klpart = (double*)(base + SL.klpart);
@@ -298,6 +300,137 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
         CU(cudaMemcpyAsync(status + i0, s + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (want_grad) {
             CU(cudaMemcpyAsync(grad_hyp + (size_t)i0 * 4, s + o_gh, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, s + o_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+    }
+    h->max_slots = saved_slots;
+    return rc;
+}
+
+// ---- inducing-point bounds --------------------------------------------------------------------------------------
+int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, const double* t, const double* Z, const double* Y,
+                         int nY, const int* item_gene, const double* b, const double* prior, const double* hyp,
+                         int kernel_kind, int model, int multi, const double* logPhi, int want_grad, double* elbo,
+                         double* grad_hyp, double* grad_b, double* grad_logPhi, int* status, void* cuda_stream) {
+    if (!h) return BGP_ERR_ARG;
+    if (count <= 0 || N <= 0 || Dtot <= 0 || nY <= 0 || Mz <= 0) return fail(h, BGP_ERR_ARG, "count, N, Dtot, nY, Mz must be positive");
+    if (Mz > SP_MAX_MZ) return fail(h, BGP_ERR_ARG, "Mz = %d exceeds the supported maximum of %d inducing rows", Mz, SP_MAX_MZ);
+    if (!t || !Z || !Y || !item_gene || !b || !prior || !hyp || !logPhi || !elbo || !status) return fail(h, BGP_ERR_ARG, "null input pointer");
+    if (want_grad && (!grad_hyp || !grad_logPhi)) return fail(h, BGP_ERR_ARG, "want_grad needs grad_hyp and grad_logPhi");
+    if (kernel_kind != BGP_KERNEL_MATERN32 && kernel_kind != BGP_KERNEL_SQEXP) return fail(h, BGP_ERR_ARG, "unknown kernel kind %d", kernel_kind);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int SD = multi ? Dtot : 1, D = multi ? 1 : Dtot;
+    const int M = 3 * N, Mp = (M + SP_SL - 1) / SP_SL * SP_SL;
+    const int nch = (N + PHI_RCH - 1) / PHI_RCH;
+    const int nslab = Mp / SP_SL;
+    // items per wave: bounded by memory; column splits so that a wave fills the GPU about twice
+    auto slot_bytes_for = [&](int nsplit) { return (size_t)sparse_layout(N, Mp, Mz, D, nsplit, nch).total * 8; };
+    int items_cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
+    if (items_cap > count) items_cap = count;
+    int nsplit = (2 * h->sm_count + items_cap * SD - 1) / (items_cap * SD);
+    if (nsplit > 16) nsplit = 16;
+    if (nsplit > nslab) nsplit = nslab;
+    if (nsplit < 1) nsplit = 1;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = (size_t)(0.9 * (double)(free_b + h->ws_bytes));
+    const size_t per_item = slot_bytes_for(nsplit) * SD + (size_t)SD * 64;
+    if ((size_t)items_cap * per_item > avail) items_cap = (int)(avail / per_item);
+    if (items_cap < 1) return fail(h, BGP_ERR_NOMEM, "one sparse work item at N=%d, Mz=%d needs %zu bytes of workspace", N, Mz, per_item);
+    const SparseLayout SL = sparse_layout(N, Mp, Mz, D, nsplit, nch);
+    const size_t sub_out_off = align_up((size_t)items_cap * SD * SL.total * 8, 256);
+    int rc = ensure_ws(h, sub_out_off + (size_t)items_cap * SD * 64);
+    if (rc != BGP_OK) return rc;
+    double* wsd = (double*)h->ws;
+    double* sub_out = (double*)((char*)h->ws + sub_out_off);
+
+    SparseParams P;
+    memset(&P, 0, sizeof(P));
+    P.N = N; P.M = M; P.Mp = Mp; P.Mz = Mz; P.D = D; P.nch = nch; P.nsplit = nsplit; P.SD = SD; P.Dtot = Dtot;
+    P.kind = kernel_kind; P.model = model; P.want_grad = want_grad; P.square_noise = 1e-6; P.kl_weight = 1.0;
+    P.slot_stride = SL.total;
+    P.t = t; P.Z = Z; P.hyp = hyp; P.bv = b; P.Y = Y; P.item_gene = item_gene;
+    P.ws = wsd; P.status = status; P.elbo = elbo; P.grad_hyp = want_grad ? grad_hyp : nullptr; P.grad_b = want_grad ? grad_b : nullptr;
+
+    PhiParams F;
+    memset(&F, 0, sizeof(F));
+    F.N = N; F.M = M; F.Mp = Mp; F.D = D; F.nch = nch; F.model = model; F.kl_weight = 1.0; F.SD = SD; F.Dtot = Dtot;
+    F.slot_stride = SL.total;
+    F.logPhi = logPhi; F.t = t; F.prior = prior; F.bv = b; F.Y = Y; F.item_gene = item_gene;
+    F.lse = wsd + SL.lse; F.Apart = wsd + SL.Apart; F.vpart = wsd + SL.vpart; F.klpart = wsd + SL.klpart;
+    F.Abar = wsd + SL.Abar; F.vbar = wsd + SL.vbar; F.grad_logPhi = grad_logPhi;
+
+    for (int item0 = 0; item0 < count; item0 += items_cap) {
+        const int n = (count - item0 < items_cap) ? (count - item0) : items_cap;
+        const int nslots = n * SD;
+        P.item0 = item0; F.item0 = item0;
+        phi_launch_forward(F, nslots, st);
+        h->launches++;
+        for (int phase = 0; phase <= 5; ++phase) {
+            if (phase == 4 && !want_grad) continue;
+            sparse_launch_phase(P, nslots, phase, sub_out, st);
+            h->launches += (phase == 5) ? 2 : 1;
+        }
+        if (want_grad) { phi_launch_backward(F, n, st); h->launches++; }
+        CU(cudaGetLastError());
+    }
+    return BGP_OK;
+}
+
+int bgp_sparse_elbo_grad_host(bgp_handle* h, int count, int N, int Dtot, int Mz, const double* t, const double* Z,
+                              const double* Y, int nY, const int* item_gene, const double* b, const double* prior,
+                              const double* hyp, int kernel_kind, int model, int multi, const double* logPhi, int want_grad,
+                              double* elbo, double* grad_hyp, double* grad_b, double* grad_logPhi, int* status) {
+    if (!h) return BGP_ERR_ARG;
+    if (count <= 0 || N <= 0 || Dtot <= 0 || nY <= 0 || Mz <= 0) return fail(h, BGP_ERR_ARG, "count, N, Dtot, nY, Mz must be positive");
+    CU(cudaSetDevice(h->device));
+    const size_t M = 3 * (size_t)N;
+    const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
+    const int SD = multi ? Dtot : 1;
+    const size_t per_item = (size_t)N * M * 8;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = free_b + h->ws_bytes + h->stage_bytes;
+    int cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
+    // half of the memory for staging (logPhi + gradient), the rest for the workspace
+    if ((size_t)cap * 2 * per_item > (size_t)(0.45 * (double)avail)) cap = (int)((size_t)(0.45 * (double)avail) / (2 * per_item));
+    if (cap < 1) return fail(h, BGP_ERR_NOMEM, "one sparse work item at N=%d does not fit in device memory", N);
+    if (cap > count) cap = count;
+    const int saved_slots = h->max_slots;
+    h->max_slots = cap;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t o_t = take((size_t)N * 8), o_Z = take((size_t)Mz * 16), o_Y = take((size_t)nY * N * Dtot * 8);
+    const size_t o_prior = take((size_t)N * pcols * 8);
+    const size_t o_gene = take((size_t)cap * 4), o_b = take((size_t)cap * SD * 8), o_hyp = take((size_t)cap * 24);
+    const size_t o_elbo = take((size_t)cap * 8), o_gh = take((size_t)cap * 24), o_gb = take((size_t)cap * SD * 8), o_st = take((size_t)cap * 4);
+    const size_t o_lp = take((size_t)cap * per_item), o_g = take(want_grad ? (size_t)cap * per_item : 0);
+    int rc = ensure_stage(h, o);
+    if (rc != BGP_OK) { h->max_slots = saved_slots; return rc; }
+    char* s = (char*)h->stage;
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(s + o_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s + o_Z, Z, (size_t)Mz * 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s + o_Y, Y, (size_t)nY * N * Dtot * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s + o_prior, prior, (size_t)N * pcols * 8, cudaMemcpyHostToDevice, st));
+    for (int i0 = 0; i0 < count && rc == BGP_OK; i0 += cap) {
+        const int n = (count - i0 < cap) ? (count - i0) : cap;
+        CU(cudaMemcpyAsync(s + o_gene, item_gene + i0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s + o_b, b + (size_t)i0 * SD, (size_t)n * SD * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s + o_hyp, hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s + o_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, st));
+        rc = bgp_sparse_elbo_grad(h, n, N, Dtot, Mz, (double*)(s + o_t), (double*)(s + o_Z), (double*)(s + o_Y), nY, (int*)(s + o_gene),
+                                  (double*)(s + o_b), (double*)(s + o_prior), (double*)(s + o_hyp), kernel_kind, model, multi,
+                                  (double*)(s + o_lp), want_grad, (double*)(s + o_elbo), (double*)(s + o_gh), (double*)(s + o_gb),
+                                  want_grad ? (double*)(s + o_g) : nullptr, (int*)(s + o_st), st);
+        if (rc != BGP_OK) break;
+        CU(cudaMemcpyAsync(elbo + i0, s + o_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(status + i0, s + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (want_grad) {
+            CU(cudaMemcpyAsync(grad_hyp + (size_t)i0 * 3, s + o_gh, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+            if (grad_b) CU(cudaMemcpyAsync(grad_b + (size_t)i0 * SD, s + o_gb, (size_t)n * SD * 8, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, s + o_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
         }
         CU(cudaStreamSynchronize(st));

@@ -2,6 +2,7 @@
 #pragma once
 #include "bgp_dense.cuh"
 #include "bgp_phi.cuh"
+#include "bgp_sparse.cuh"
 
 namespace bgp {
 cudaError_t dense_init_kernels();
@@ -9,5 +10,7 @@ void dense_launch_prep(const DenseParams& P, const double* Apart, const double* 
                        const int* item_gene, int nitems, cudaStream_t st);
 void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_t st);
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st);
+cudaError_t sparse_init_kernels();
+void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* sub_out, cudaStream_t st);
 void phi_launch_gather(const double* logPhi, double* phi, int count, int N, cudaStream_t st);
 }  // namespace bgp

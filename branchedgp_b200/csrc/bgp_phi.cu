@@ -43,12 +43,12 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     __shared__ double Ys[PHI_RCH][PHI_DCH];
     __shared__ double red[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk = blockIdx.x, slot = blockIdx.y, item = P.item0 + slot;
+    const int chunk = blockIdx.x, slot = blockIdx.y, item = P.item0 + slot / P.SD, ycol = (P.SD > 1) ? slot % P.SD : 0;
     const int N = P.N, M = P.M, Mp = P.Mp, D = P.D;
     const int r0 = chunk * PHI_RCH;
     const int nr = min(PHI_RCH, N - r0);
     const double* lp = P.logPhi + ((size_t)item * N + r0) * M;
-    const double b = P.bv[item];
+    const double b = P.bv[(size_t)P.item0 * P.SD + slot];
     // ---- row log-sum-exp, one warp per row
     for (int rr = warp; rr < nr; rr += NTHREADS / 32) {
         const double* row = lp + (size_t)rr * M;
@@ -67,14 +67,14 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     __syncthreads();
     // ---- column pass: thread per column, rows of the chunk in the inner loop
     const double log_eps = log(1e-6);
-    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * D;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot + ycol;
     double kl = 0.0;
     for (int d0 = 0; d0 < D; d0 += PHI_DCH) {
         const int nd = min(PHI_DCH, D - d0);
         __syncthreads();
         if (tid < PHI_RCH * PHI_DCH) {
             const int rr = tid / PHI_DCH, dd = tid % PHI_DCH;
-            Ys[rr][dd] = (rr < nr && dd < nd) ? Yg[(size_t)(r0 + rr) * D + d0 + dd] : 0.0;
+            Ys[rr][dd] = (rr < nr && dd < nd) ? Yg[(size_t)(r0 + rr) * P.Dtot + d0 + dd] : 0.0;
         }
         __syncthreads();
         for (int j = tid; j < Mp; j += NTHREADS) {
@@ -101,36 +101,50 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     if (tid == 0) P.klpart[(size_t)slot * P.slot_stride + chunk] = kl;
 }
 
+// grid (row chunks, ITEMS of the wave): sums the contributions of the item's SD sub-problems.
 __global__ void __launch_bounds__(NTHREADS) k_phi_backward(PhiParams P) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk = blockIdx.x, slot = blockIdx.y, item = P.item0 + slot;
-    const int N = P.N, M = P.M, Mp = P.Mp, D = P.D;
+    const int chunk = blockIdx.x, litem = blockIdx.y, item = P.item0 + litem;
+    const int N = P.N, M = P.M, Mp = P.Mp, D = P.D, SD = P.SD;
     const int r0 = chunk * PHI_RCH;
     const int nr = min(PHI_RCH, N - r0);
-    const double b = P.bv[item];
     const double log_eps = log(1e-6);
-    const double* Abar = P.Abar + (size_t)slot * P.slot_stride;
-    const double* vbar = P.vbar + (size_t)slot * P.slot_stride;
-    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * D;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* bvi = P.bv + (size_t)item * SD;
+    const size_t slot0 = (size_t)litem * SD;
     for (int rr = warp; rr < nr; rr += NTHREADS / 32) {
         const int row = r0 + rr;
         const double* x = P.logPhi + ((size_t)item * N + row) * M;
         double* gout = P.grad_logPhi + ((size_t)item * N + row) * M;
-        const bool act = P.t[row] > b;
-        if (P.model == MODEL_MBGP && !act) {   // trunk rows of MBGP use the constant phiTrunk: no gradient
+        const double ti = P.t[row];
+        // sub-problems in which this row is a free (softmax) row; BGP rows are always free, MBGP trunk rows
+        // (t_i <= b_d) use the constant phiTrunk and carry no gradient
+        int nact = 0;
+        for (int sd = 0; sd < SD; ++sd) nact += (P.model == MODEL_BGP || ti > bvi[sd]) ? 1 : 0;
+        if (nact == 0) {
             for (int j = lane; j < M; j += 32) gout[j] = 0.0;
             continue;
         }
-        const double l = P.lse[(size_t)slot * P.slot_stride + row];
+        const bool act0 = ti > bvi[0];   // BGP: selects the trunk / branch form of pZ;  MBGP active rows: always the eZ0 form
+        const double l = P.lse[slot0 * P.slot_stride + row];
         double r = 0.0;
         for (int j = lane; j < M; j += 32) {
             const int cell = j / 3, f = j - 3 * cell;
             const bool inblock = (cell == row);
             const double S = exp(x[j] - l);
             const double phi = SQ_A * S + SQ_B;
-            double yv = 0.0;
-            for (int d = 0; d < D; ++d) yv += Yg[(size_t)row * D + d] * vbar[(size_t)d * Mp + j];
-            const double sb = SQ_A * (Abar[j] + yv - P.kl_weight * (log(phi) + 1.0 - log_pz(P.model, act, inblock, f, P.prior, row, log_eps)));
+            double acc = 0.0;
+            for (int sd = 0; sd < SD; ++sd) {
+                if (!(P.model == MODEL_BGP || ti > bvi[sd])) continue;
+                const double* Abar = P.Abar + (slot0 + sd) * P.slot_stride;
+                const double* vbar = P.vbar + (slot0 + sd) * P.slot_stride;
+                const int yc = (SD > 1) ? sd : 0;
+                double yv = 0.0;
+                for (int d = 0; d < D; ++d) yv += Yg[(size_t)row * P.Dtot + yc + d] * vbar[(size_t)d * Mp + j];
+                acc += Abar[j] + yv;
+            }
+            const double lpz = log_pz(P.model, P.model == MODEL_BGP ? act0 : true, inblock, f, P.prior, row, log_eps);
+            const double sb = SQ_A * (acc - P.kl_weight * (double)nact * (log(phi) + 1.0 - lpz));
             gout[j] = sb;
             r += S * sb;
         }
@@ -142,8 +156,9 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_backward(PhiParams P) {
     }
 }
 
-void phi_launch_forward(const PhiParams& P, int nitems, cudaStream_t st) {
-    dim3 grid(P.nch, nitems);
+// nsubs = sub-problems (slots) in the wave;  nitems = nsubs / SD
+void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
+    dim3 grid(P.nch, nsubs);
     k_phi_forward<<<grid, NTHREADS, 0, st>>>(P);
 }
 void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {

@@ -6,16 +6,21 @@ namespace bgp {
 
 constexpr int PHI_RCH = 16;   // rows of logPhi handled by one CTA of the forward pass
 
+// A "sub-problem" is one (work item, output group): dense / sparse BGP have one per item carrying all D outputs
+// (SD = 1, D = Dtot); the MBGP multi-output bound has one per output (SD = Dtot, D = 1) because the trunk mask
+// t_i > b_d differs per output (MBGP/assigngp.py:217-251).  Workspace slot s of a wave is sub-problem s; the slots of
+// one item are contiguous.
 struct PhiParams {
     int N, M, Mp, D, nch, model;
+    int SD, Dtot;              // sub-problems per item; outputs per item (row length of Y)
     int item0;
     long long slot_stride;     // doubles between consecutive slots for lse / Apart / vpart / klpart / Abar / vbar
     double kl_weight;
     const double* logPhi;      // [count][N][M] row-major (M = 3N, cell-major columns 3*cell + f)
     const double* t;           // [N] pseudotime
     const double* prior;       // BGP: [N][2] phiPrior;  MBGP: [N][3]
-    const double* bv;          // [count] branching point used for the trunk / branch split (t <= b  => trunk)
-    const double* Y;           // [nY][N][D]
+    const double* bv;          // [count][SD] branching point used for the trunk / branch split (t <= b  => trunk)
+    const double* Y;           // [nY][N][Dtot]
     const int* item_gene;      // [count]
     double* lse;               // [slot][N]  row log-sum-exp of logPhi
     // forward outputs (per slot, partial over row chunks; reduced by the consumer in a fixed order => deterministic)

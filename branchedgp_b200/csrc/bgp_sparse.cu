@@ -1,0 +1,544 @@
+// Inducing-point AssignGP bounds and gradients (sparse BGP, MBGP multi-output), sm_100a.
+//
+//   Kuu = K(Z,Z) + (noise + jitter) I,  L = chol(Kuu),  V = L^-1 K(Z,X),  P = V Delta V^T + I,  R = chol(P),
+//   c = R^-1 V (Phi^T Y) / s,  bound = trace - N D/2 log(2 pi s) - D/2 sum log R_ii^2 - sum Y^2 / (2 s) + sum c^2 / 2 - KL
+//   (assigngp_denseSparse.py:59-107; MBGP/assigngp.py:492-558 sums this over outputs with per-output b_d and masks);
+//   gradient = SURVEY.md App. B.2.
+// Matrices are Mz x Mz (Mz = 30 for BGP, 180 for MBGP): they are factored / inverted in shared memory (packed lower
+// triangle) by one CTA per sub-problem, while the 3N columns of X are streamed in slabs of 32 with K(Z, x_j) generated
+// in-kernel.  The O(N * 3N) assignment passes (bgp_phi.cu) dominate at the sizes the reference uses.
+#include "bgp_sparse.cuh"
+#include "bgp_dense.cuh"
+#include "bgp_launch.h"
+
+namespace bgp {
+
+#define SP_SETUP()                                                                                            \
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                                            \
+    const int slot = blockIdx.y;                                                                              \
+    const int item = P.item0 + slot / P.SD;                                                                   \
+    const int sd = slot % P.SD;                                                                               \
+    const int Mz = P.Mz, Mp = P.Mp, M = P.M, N = P.N, D = P.D;                                                \
+    const SparseLayout SLy = sparse_layout(N, Mp, Mz, D, P.nsplit, P.nch);                                    \
+    double* const ws = P.ws + (size_t)slot * P.slot_stride;                                                   \
+    const double ell = P.hyp[(size_t)item * 3 + 0], kvar = P.hyp[(size_t)item * 3 + 1], likvar = P.hyp[(size_t)item * 3 + 2]; \
+    const double bpt = P.bv[(size_t)item * P.SD + sd];                                                        \
+    const double kinv = 1.0 / (kvar + JITTER);                                                                \
+    (void)tid; (void)warp; (void)lane; (void)sd; (void)M; (void)N; (void)D; (void)ell; (void)kvar; (void)likvar; (void)bpt; (void)kinv; (void)ws;
+
+__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, j <= i
+
+// In-place lower Cholesky of a packed matrix in shared memory.
+__device__ void chol_packed(double* A, int n, int& fail) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < n; ++j) {
+        __syncthreads();
+        double d = A[pk(j, j)];
+        if (!(d > 0.0)) { if (fail == 0) fail = j + 1; d = 1.0; }
+        const double r = sqrt(d);
+        __syncthreads();
+        if (tid == 0) A[pk(j, j)] = r;
+        for (int i = j + 1 + tid; i < n; i += nt) A[pk(i, j)] /= r;
+        __syncthreads();
+        for (int i = j + 1 + (tid >> 4); i < n; i += nt >> 4) {
+            const double lij = A[pk(i, j)];
+            for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[pk(i, k)] -= lij * A[pk(k, j)];
+        }
+    }
+    __syncthreads();
+}
+
+// In-place inverse of a packed lower-triangular matrix in shared memory (two threads per column).
+__device__ void trinv_packed(double* A, int n) {
+    const int tid = threadIdx.x;
+    const int nt = blockDim.x;
+    for (int i = 0; i < n; ++i) {
+        const double lii = A[pk(i, i)];
+        for (int j0 = 0; j0 <= i; j0 += nt / 2) {   // columns handled in rounds when n > nt/2
+            const int j = j0 + (tid >> 1), h = tid & 1;
+            double s = 0.0;
+            if (j < i)
+                for (int k = j + h; k < i; k += 2) s += A[pk(i, k)] * A[pk(k, j)];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            const double x = (j < i) ? (-s / lii) : (1.0 / lii);
+            __syncthreads();
+            if (h == 0 && j <= i) A[pk(i, j)] = x;
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- k_sp_prep
+__global__ void __launch_bounds__(NTHREADS) k_sp_prep(SparseParams P) {
+    SP_SETUP();
+    __shared__ double red[32];
+    const int nch = P.nch;
+    double suma = 0.0;
+    for (int j = tid; j < Mp; j += NTHREADS) {
+        double a = 0.0;
+        if (j < M)
+            for (int ch = 0; ch < nch; ++ch) a += ws[SLy.Apart + (size_t)ch * Mp + j];
+        ws[SLy.A + j] = a;
+        ws[SLy.Delta + j] = a / likvar;
+        suma += a;
+        for (int d = 0; d < D; ++d) {
+            double s = 0.0;
+            if (j < M)
+                for (int ch = 0; ch < nch; ++ch) s += ws[SLy.vpart + ((size_t)ch * D + d) * Mp + j];
+            ws[SLy.v + (size_t)d * Mp + j] = s;
+        }
+    }
+    for (int i = tid; i < N; i += NTHREADS) {
+        double k, dl, dd;
+        kbase_grads(P.t[i] - bpt, ell, kvar, P.kind, k, dl, dd);
+        ws[SLy.kax + i] = k; ws[SLy.dkalx + i] = dl; ws[SLy.dkabx + i] = -dd;
+    }
+    for (int m = tid; m < Mz; m += NTHREADS) {
+        double k, dl, dd;
+        kbase_grads(P.Z[2 * m] - bpt, ell, kvar, P.kind, k, dl, dd);
+        ws[SLy.kaz + m] = k; ws[SLy.dkalz + m] = dl; ws[SLy.dkabz + m] = -dd;
+    }
+    suma = block_sum(suma, red);
+    double kl = 0.0;
+    for (int ch = tid; ch < nch; ch += NTHREADS) kl += ws[SLy.klpart + ch];
+    kl = block_sum(kl, red);
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot + (P.SD > 1 ? sd : 0);
+    double y2 = 0.0;
+    for (int e = tid; e < N * D; e += NTHREADS) { const double y = Yg[(size_t)(e / D) * P.Dtot + (e % D)]; y2 += y * y; }
+    y2 = block_sum(y2, red);
+    if (tid == 0) {
+        ws[SLy.scal + SS_KL] = kl; ws[SLy.scal + SS_SUMY2] = y2; ws[SLy.scal + SS_SUMA] = suma;
+        if (sd == 0) P.status[item] = 0;
+    }
+}
+
+// covariance between inducing row m and column j of X (cell-major), branch_kernParamGPflow.py:117-198
+__device__ __forceinline__ double kuf_entry(const SparseParams& P, const double* ws, const SparseLayout& SLy, int m, int j, double ell,
+                                            double kvar, double kinv) {
+    const int cell = j / 3, f = j - 3 * cell;
+    const int fz = (int)P.Z[2 * m + 1] - 1;
+    if (fz == f) return kbase(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind);
+    return (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
+}
+
+// ---------------------------------------------------------------------------------------------------- k_sp_kuu
+__global__ void __launch_bounds__(NTHREADS) k_sp_kuu(SparseParams P) {
+    SP_SETUP();
+    extern __shared__ __align__(16) double sm[];
+    int fail = 0;
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        if (n > m) continue;
+        const int fm = (int)P.Z[2 * m + 1], fn = (int)P.Z[2 * n + 1];
+        double k = (fm == fn) ? kbase(P.Z[2 * m] - P.Z[2 * n], ell, kvar, P.kind) : (ws[SLy.kaz + m] * kinv) * ws[SLy.kaz + n];
+        if (m == n) k += P.square_noise + JITTER;   // White / noise_level 1e-6 + jitter 1e-6 (assigngp_denseSparse.py:72-75)
+        sm[pk(m, n)] = k;
+    }
+    __syncthreads();
+    chol_packed(sm, Mz, fail);
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        ws[SLy.L + e] = (n <= m) ? sm[pk(m, n)] : 0.0;
+    }
+    __syncthreads();
+    trinv_packed(sm, Mz);
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        const double x = (n <= m) ? sm[pk(m, n)] : 0.0;
+        ws[SLy.Linv + e] = x;
+        ws[SLy.LinvT + (size_t)n * Mz + m] = x;
+    }
+    if (tid == 0 && fail != 0) atomicCAS(&P.status[item], 0, fail);
+}
+
+// ---------------------------------------------------------------------------------------------------- k_sp_fwd
+// grid (nsplit, slots).  V = Linv Kuf for this CTA's slabs; partial P = V Delta V^T, z = V v, trace.
+__global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
+    SP_SETUP();
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int LDS_ = SP_SL + 1;
+    double* Ks = sm;                       // [Mz][33]  K(Z, x_j) of the slab
+    double* Vs = sm + (size_t)Mz * LDS_;   // [Mz][33]  V of the slab
+    double* Dls = Vs + (size_t)Mz * LDS_;  // [32] Delta of the slab
+    const int split = blockIdx.x, nsplit = P.nsplit;
+    const double* Linv = ws + SLy.Linv;
+    double* Pp = ws + SLy.Ppart + (size_t)split * Mz * Mz;
+    double* zp = ws + SLy.zpart + (size_t)split * D * Mz;
+    const int nslab = (M + SP_SL - 1) / SP_SL;
+    double tr = 0.0;
+    bool first = true;
+    for (int sl = split; sl < nslab || first; sl += nsplit) {
+        const bool empty = sl >= nslab;   // a split without slabs still zero-initialises its partials
+        const int j0 = sl * SP_SL;
+        __syncthreads();
+        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
+            Ks[m * LDS_ + jj] = (!empty && j < M) ? kuf_entry(P, ws, SLy, m, j, ell, kvar, kinv) : 0.0;
+        }
+        if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
+        __syncthreads();
+        for (int m = warp; m < Mz; m += NTHREADS / 32) {
+            const double* lr = Linv + (size_t)m * Mz;
+            double s = 0.0;
+            for (int k = 0; k <= m; ++k) s += lr[k] * Ks[k * LDS_ + lane];
+            Vs[m * LDS_ + lane] = s;
+            if (!empty && j0 + lane < Mp) ws[SLy.V + (size_t)m * Mp + j0 + lane] = s;
+            tr += Dls[lane] * s * s;
+        }
+        __syncthreads();
+        // Ks <- Delta_j V (scaled copy) so that P += Ks Vs^T
+        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            const int m = e / SP_SL, jj = e % SP_SL;
+            Ks[m * LDS_ + jj] = Dls[jj] * Vs[m * LDS_ + jj];
+        }
+        __syncthreads();
+        for (int m = warp; m < Mz; m += NTHREADS / 32)
+            for (int n = lane; n <= m; n += 32) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int jj = 0; jj < SP_SL; ++jj) s += Ks[m * LDS_ + jj] * Vs[n * LDS_ + jj];
+                double* dst = Pp + (size_t)m * Mz + n;
+                *dst = first ? s : (*dst + s);
+            }
+        for (int e = tid; e < D * Mz; e += NTHREADS) {
+            const int d = e / Mz, m = e % Mz;
+            double s = 0.0;
+            if (!empty)
+                for (int jj = 0; jj < SP_SL; ++jj)
+                    if (j0 + jj < M) s += Vs[m * LDS_ + jj] * ws[SLy.v + (size_t)d * Mp + j0 + jj];
+            zp[e] = first ? s : (zp[e] + s);
+        }
+        first = false;
+    }
+    tr = block_sum(tr, red);
+    if (tid == 0) ws[SLy.hpart + (size_t)split * 8 + 0] = tr;
+}
+
+// ---------------------------------------------------------------------------------------------------- k_sp_mid
+__global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
+    SP_SETUP();
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    int fail = 0;
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        if (n > m) continue;
+        double s = (m == n) ? 1.0 : 0.0;
+        for (int sp = 0; sp < P.nsplit; ++sp) s += ws[SLy.Ppart + (size_t)sp * Mz * Mz + e];
+        sm[pk(m, n)] = s;
+    }
+    __syncthreads();
+    chol_packed(sm, Mz, fail);
+    double ld = 0.0;
+    for (int m = tid; m < Mz; m += NTHREADS) { const double r = sm[pk(m, m)]; ld += log(r * r); }
+    ld = block_sum(ld, red);
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        ws[SLy.R + e] = (n <= m) ? sm[pk(m, n)] : 0.0;
+    }
+    __syncthreads();
+    trinv_packed(sm, Mz);   // sm = R^-1 (packed)
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        ws[SLy.Rinv + e] = (n <= m) ? sm[pk(m, n)] : 0.0;
+    }
+    // z, c = R^-1 z / s, q = R^-T c, zbar = q / s
+    double c2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+        double* z = ws + SLy.z + (size_t)d * Mz;
+        double* cv = ws + SLy.c + (size_t)d * Mz;
+        double* q = ws + SLy.q + (size_t)d * Mz;
+        double* zb = ws + SLy.zbar + (size_t)d * Mz;
+        for (int m = tid; m < Mz; m += NTHREADS) {
+            double s = 0.0;
+            for (int sp = 0; sp < P.nsplit; ++sp) s += ws[SLy.zpart + ((size_t)sp * D + d) * Mz + m];
+            z[m] = s;
+        }
+        __syncthreads();
+        for (int m = tid; m < Mz; m += NTHREADS) {
+            double s = 0.0;
+            for (int k = 0; k <= m; ++k) s += sm[pk(m, k)] * z[k];
+            s /= likvar;
+            cv[m] = s;
+            c2 += s * s;
+        }
+        __syncthreads();
+        for (int m = tid; m < Mz; m += NTHREADS) {
+            double s = 0.0;
+            for (int k = m; k < Mz; ++k) s += sm[pk(k, m)] * cv[k];
+            q[m] = s;
+            zb[m] = s / likvar;
+        }
+        __syncthreads();
+    }
+    c2 = block_sum(c2, red);
+    // Pbar = -D/2 R^-T R^-1 - 1/2 q q^T   (full symmetric)
+    const double hD = 0.5 * (double)D;
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        if (n > m) continue;
+        double s = 0.0;
+        for (int k = m; k < Mz; ++k) s += sm[pk(k, m)] * sm[pk(k, n)];
+        double qq = 0.0;
+        for (int d = 0; d < D; ++d) qq += ws[SLy.q + (size_t)d * Mz + m] * ws[SLy.q + (size_t)d * Mz + n];
+        const double pb = -hD * s - 0.5 * qq;
+        ws[SLy.Pbar + (size_t)m * Mz + n] = pb;
+        ws[SLy.Pbar + (size_t)n * Mz + m] = pb;
+    }
+    if (tid == 0) {
+        ws[SLy.scal + SS_LOGDET] = ld;
+        ws[SLy.scal + SS_SUMC2] = c2;
+        if (fail != 0) atomicCAS(&P.status[item], 0, fail + Mz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- k_sp_bwd
+// grid (nsplit, slots).  Per slab: U = Pbar V, delta, Abar, vbar, Vbar, Kuf_bar = Linv^T Vbar, partial Lbar, hyper-gradient of Kuf.
+__global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
+    SP_SETUP();
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int LDS_ = SP_SL + 1;
+    double* Vs = sm;                        // V slab
+    double* Us = sm + (size_t)Mz * LDS_;    // U, then Vbar
+    double* Gs = Us + (size_t)Mz * LDS_;    // Kuf_bar
+    double* Dls = Gs + (size_t)Mz * LDS_;   // Delta slab [32]
+    const int split = blockIdx.x, nsplit = P.nsplit;
+    const double* Pbar = ws + SLy.Pbar;
+    const double* LinvT = ws + SLy.LinvT;
+    double* Lp = ws + SLy.Lbpart + (size_t)split * Mz * Mz;
+    const int nslab = (M + SP_SL - 1) / SP_SL;
+    const double kdiag = kvar + P.square_noise;
+    double adel = 0.0, gl = 0.0, gv = 0.0, gb = 0.0;
+    bool first = true;
+    for (int sl = split; sl < nslab || first; sl += nsplit) {
+        const bool empty = sl >= nslab;
+        const int j0 = sl * SP_SL;
+        __syncthreads();
+        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
+            Vs[m * LDS_ + jj] = (!empty && j < M) ? ws[SLy.V + (size_t)m * Mp + j] : 0.0;
+        }
+        if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
+        __syncthreads();
+        for (int m = warp; m < Mz; m += NTHREADS / 32) {
+            const double* pr = Pbar + (size_t)m * Mz;
+            double s = 0.0;
+            for (int k = 0; k < Mz; ++k) s += pr[k] * Vs[k * LDS_ + lane];
+            Us[m * LDS_ + lane] = s;
+        }
+        __syncthreads();
+        if (tid < SP_SL && !empty && j0 + tid < M) {
+            const int j = j0 + tid;
+            double vu = 0.0, vv = 0.0;
+            for (int m = 0; m < Mz; ++m) { const double x = Vs[m * LDS_ + tid]; vu += x * Us[m * LDS_ + tid]; vv += x * x; }
+            const double dlt = vu + 0.5 * vv - 0.5 * kdiag;
+            ws[SLy.Abar + j] = dlt / likvar;
+            adel += ws[SLy.A + j] * dlt;
+            for (int d = 0; d < D; ++d) {
+                double s = 0.0;
+                for (int m = 0; m < Mz; ++m) s += Vs[m * LDS_ + tid] * ws[SLy.zbar + (size_t)d * Mz + m];
+                ws[SLy.vbar + (size_t)d * Mp + j] = s;
+            }
+        }
+        __syncthreads();
+        // Vbar = 2 Delta U + zbar v^T + Delta V
+        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
+            double zv = 0.0;
+            if (!empty && j < M)
+                for (int d = 0; d < D; ++d) zv += ws[SLy.zbar + (size_t)d * Mz + m] * ws[SLy.v + (size_t)d * Mp + j];
+            Us[m * LDS_ + jj] = Dls[jj] * (2.0 * Us[m * LDS_ + jj] + Vs[m * LDS_ + jj]) + zv;
+        }
+        __syncthreads();
+        // Kuf_bar[k][j] = sum_{m >= k} Linv[m][k] Vbar[m][j]
+        for (int k = warp; k < Mz; k += NTHREADS / 32) {
+            const double* lc = LinvT + (size_t)k * Mz;
+            double s = 0.0;
+            for (int m = k; m < Mz; ++m) s += lc[m] * Us[m * LDS_ + lane];
+            Gs[k * LDS_ + lane] = s;
+        }
+        __syncthreads();
+        // hyper-gradient through K(Z, X)
+        if (!empty)
+            for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+                const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
+                if (j >= M) continue;
+                const double w = Gs[m * LDS_ + jj];
+                const int cell = j / 3, f = j - 3 * cell;
+                const int fz = (int)P.Z[2 * m + 1] - 1;
+                if (fz == f) {
+                    double k, dl, dd;
+                    kbase_grads(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind, k, dl, dd);
+                    gl += w * dl;
+                    gv += w * k / kvar;
+                } else {
+                    const double a = ws[SLy.kaz + m], b = ws[SLy.kax + cell];
+                    gl += w * (ws[SLy.dkalz + m] * b + a * ws[SLy.dkalx + cell]) * kinv;
+                    gv += w * ((a * kinv) * b) * (2.0 / kvar - kinv);
+                    gb += w * (ws[SLy.dkabz + m] * b + a * ws[SLy.dkabx + cell]) * kinv;
+                }
+            }
+        // Lbar partial = -tril(Kuf_bar V^T)
+        for (int m = warp; m < Mz; m += NTHREADS / 32)
+            for (int n = lane; n <= m; n += 32) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int jj = 0; jj < SP_SL; ++jj) s += Gs[m * LDS_ + jj] * Vs[n * LDS_ + jj];
+                double* dst = Lp + (size_t)m * Mz + n;
+                *dst = first ? -s : (*dst - s);
+            }
+        first = false;
+    }
+    adel = block_sum(adel, red);
+    gl = block_sum(gl, red);
+    gv = block_sum(gv, red);
+    gb = block_sum(gb, red);
+    if (tid == 0) {
+        double* hp = ws + SLy.hpart + (size_t)split * 8;
+        hp[1] = adel; hp[2] = gl; hp[3] = gv; hp[4] = gb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- k_sp_end
+// Cholesky adjoint of Kuu (Kuu_bar = sym(Linv^T Phi(L^T Lbar) Linv)), hyper-gradient through K(Z,Z), assembly of the
+// sub-problem's bound and gradient.  outputs: sub_out[slot][8] = elbo, g_ell, g_var, g_lik, g_b
+__global__ void __launch_bounds__(NTHREADS) k_sp_end(SparseParams P, double* sub_out) {
+    SP_SETUP();
+    __shared__ double red[32];
+    const double* L = ws + SLy.L;
+    const double* Linv = ws + SLy.Linv;
+    double* T = ws + SLy.T;
+    double* W = ws + SLy.W;
+    double* S = ws + SLy.S;
+    double gl = 0.0, gv = 0.0, gb = 0.0;
+    if (P.want_grad) {
+    // T = Phi(L^T Lbar): T[m][n] = sum_{k >= m} L[k][m] Lbar[k][n],  n <= m, diagonal halved
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        double s = 0.0;
+        if (n <= m) {
+            for (int k = m; k < Mz; ++k) {
+                double lb = 0.0;
+                for (int sp = 0; sp < P.nsplit; ++sp) lb += ws[SLy.Lbpart + (size_t)sp * Mz * Mz + (size_t)k * Mz + n];
+                s += L[(size_t)k * Mz + m] * lb;
+            }
+            if (n == m) s *= 0.5;
+        }
+        T[e] = s;
+    }
+    __syncthreads();
+    // W = T Linv  (lower): W[m][n] = sum_{n <= k <= m} T[m][k] Linv[k][n]
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        double s = 0.0;
+        if (n <= m)
+            for (int k = n; k <= m; ++k) s += T[(size_t)m * Mz + k] * Linv[(size_t)k * Mz + n];
+        W[e] = s;
+    }
+    __syncthreads();
+    // S = Linv^T W: S[m][n] = sum_{k >= max(m,n)} Linv[k][m] W[k][n]
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        double s = 0.0;
+        for (int k = (m > n ? m : n); k < Mz; ++k) s += Linv[(size_t)k * Mz + m] * W[(size_t)k * Mz + n];
+        S[e] = s;
+    }
+    __syncthreads();
+    // hyper-gradient through K(Z,Z): Kuu_bar = (S + S^T)/2, full sum
+    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+        const int m = e / Mz, n = e % Mz;
+        const double w = 0.5 * (S[e] + S[(size_t)n * Mz + m]);
+        const int fm = (int)P.Z[2 * m + 1], fn = (int)P.Z[2 * n + 1];
+        if (fm == fn) {
+            double k, dl, dd;
+            kbase_grads(P.Z[2 * m] - P.Z[2 * n], ell, kvar, P.kind, k, dl, dd);
+            gl += w * dl;
+            gv += w * k / kvar;
+        } else {
+            const double a = ws[SLy.kaz + m], b = ws[SLy.kaz + n];
+            gl += w * (ws[SLy.dkalz + m] * b + a * ws[SLy.dkalz + n]) * kinv;
+            gv += w * ((a * kinv) * b) * (2.0 / kvar - kinv);
+            gb += w * (ws[SLy.dkabz + m] * b + a * ws[SLy.dkabz + n]) * kinv;
+        }
+    }
+    }
+    gl = block_sum(gl, red);
+    gv = block_sum(gv, red);
+    gb = block_sum(gb, red);
+    if (tid == 0) {
+        double tr = 0.0, adel = 0.0;
+        for (int sp = 0; sp < P.nsplit; ++sp) {
+            const double* hp = ws + SLy.hpart + (size_t)sp * 8;
+            tr += hp[0];
+            if (P.want_grad) { adel += hp[1]; gl += hp[2]; gv += hp[3]; gb += hp[4]; }
+        }
+        const double s = likvar, ND = (double)N * (double)D;
+        const double suma = ws[SLy.scal + SS_SUMA], y2 = ws[SLy.scal + SS_SUMY2], c2 = ws[SLy.scal + SS_SUMC2];
+        const double kdiag = kvar + P.square_noise;
+        const double trace = -0.5 * kdiag * suma / s + 0.5 * tr;
+        const double elbo = trace - 0.5 * ND * log(2.0 * 3.14159265358979323846 * s) - 0.5 * (double)D * ws[SLy.scal + SS_LOGDET] -
+                            0.5 * y2 / s + 0.5 * c2 - P.kl_weight * ws[SLy.scal + SS_KL];
+        double* o = sub_out + (size_t)slot * 8;
+        o[0] = elbo;
+        o[1] = gl;
+        o[2] = gv - 0.5 * suma / s;
+        o[3] = -c2 / s - adel / (s * s) - 0.5 * ND / s + 0.5 * y2 / (s * s);
+        o[4] = gb;
+    }
+}
+
+// sum the SD sub-problems of every item of the wave
+__global__ void k_sp_reduce(SparseParams P, const double* sub_out, int nitems) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nitems) return;
+    const int item = P.item0 + li;
+    double e = 0.0, gl = 0.0, gv = 0.0, gs = 0.0;
+    for (int sd = 0; sd < P.SD; ++sd) {
+        const double* o = sub_out + ((size_t)li * P.SD + sd) * 8;
+        e += o[0]; gl += o[1]; gv += o[2]; gs += o[3];
+        if (P.grad_b) P.grad_b[(size_t)item * P.SD + sd] = o[4];
+    }
+    P.elbo[item] = e;
+    if (P.grad_hyp) {
+        P.grad_hyp[(size_t)item * 3 + 0] = gl;
+        P.grad_hyp[(size_t)item * 3 + 1] = gv;
+        P.grad_hyp[(size_t)item * 3 + 2] = gs;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- launchers
+static size_t packed_bytes(int Mz) { return (size_t)Mz * (Mz + 1) / 2 * 8; }
+static size_t slab_bytes(int Mz, int nbuf) { return ((size_t)nbuf * Mz * (SP_SL + 1) + SP_SL) * 8; }
+
+cudaError_t sparse_init_kernels() {
+    cudaError_t e;
+    const int big = 200 * 1024;
+    if ((e = cudaFuncSetAttribute((const void*)k_sp_kuu, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute((const void*)k_sp_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute((const void*)k_sp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute((const void*)k_sp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// phase: 0 prep, 1 Kuu, 2 forward slabs, 3 mid, 4 backward slabs, 5 end + reduce
+void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* sub_out, cudaStream_t st) {
+    dim3 g1(1, nslots), gs(P.nsplit, nslots);
+    switch (phase) {
+        case 0: k_sp_prep<<<g1, NTHREADS, 0, st>>>(P); break;
+        case 1: k_sp_kuu<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
+        case 2: k_sp_fwd<<<gs, NTHREADS, slab_bytes(P.Mz, 2), st>>>(P); break;
+        case 3: k_sp_mid<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
+        case 4: k_sp_bwd<<<gs, NTHREADS, slab_bytes(P.Mz, 3), st>>>(P); break;
+        case 5: {
+            k_sp_end<<<g1, NTHREADS, 0, st>>>(P, sub_out);
+            const int nitems = nslots / P.SD;
+            k_sp_reduce<<<(nitems + 127) / 128, 128, 0, st>>>(P, sub_out, nitems);
+            break;
+        }
+        default: break;
+    }
+}
+
+}  // namespace bgp

@@ -84,6 +84,23 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
                              int kernel_kind, int model, double kl_weight, const double* logPhi, const double* KConst,
                              int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status);
 
+/* Inducing-point bounds + gradients.
+ *   multi == 0: AssignGPSparse.maximum_log_likelihood_objective (assigngp_denseSparse.py:59-107): one branching point per
+ *               item (b[count]), all Dtot outputs share Phi; model = BGP_MODEL_BGP, prior[N][2].
+ *   multi == 1: MBGP AssignGP._build_likelihood_sparse (MBGP/assigngp.py:492-558): one branching point per OUTPUT
+ *               (b[count][Dtot]), per-output trunk masks on a shared logPhi; model = BGP_MODEL_MBGP, prior[N][3].
+ *   Z[Mz][2]    inducing inputs (time, function in {1,2,3}), Mz <= 208
+ * outputs: elbo[count], grad_hyp[count][3] (d/d lengthscale, kernel variance, likelihood variance),
+ *          grad_b[count][multi ? Dtot : 1], grad_logPhi[count][N][3N], status[count]. */
+int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, const double* t, const double* Z, const double* Y,
+                         int nY, const int* item_gene, const double* b, const double* prior, const double* hyp,
+                         int kernel_kind, int model, int multi, const double* logPhi, int want_grad, double* elbo,
+                         double* grad_hyp, double* grad_b, double* grad_logPhi, int* status, void* cuda_stream);
+int bgp_sparse_elbo_grad_host(bgp_handle* h, int count, int N, int Dtot, int Mz, const double* t, const double* Z,
+                              const double* Y, int nY, const int* item_gene, const double* b, const double* prior,
+                              const double* hyp, int kernel_kind, int model, int multi, const double* logPhi, int want_grad,
+                              double* elbo, double* grad_hyp, double* grad_b, double* grad_logPhi, int* status);
+
 /* AssignGP.GetPhi (assigngp_dense.py:130-140): softmax rows of logPhi gathered at the cell's own 3 columns -> Phi[count][N][3].
  * HOST pointers. */
 int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi);

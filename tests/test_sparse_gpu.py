@@ -1,0 +1,71 @@
+"""GPU parity tests of the inducing-point bounds (sparse BGP, MBGP multi-output) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from branchedgp_b200 import _lib
+from common import make_problem, relerr
+from oracle import bgp_numpy, host_ref
+
+pytestmark = pytest.mark.gpu
+ELBO_RTOL, GRAD_RTOL = 1e-8, 1e-6
+
+
+def _Z(Mz):
+    Z = np.ones((Mz, 2))
+    Z[:, 0] = np.linspace(0, 1, Mz, endpoint=False)
+    Z[:, 1] = np.array([i for j in range(Mz) for i in range(1, 4)])[:Mz]
+    return Z
+
+
+def _pz(pr, b):
+    return host_ref.prior_with_trunk_bgp(host_ref.expand_prior_bgp(pr["prior"]), b, pr["t"])
+
+
+@pytest.mark.parametrize("N,D,Mz,kind", [(20, 1, 10, 0), (50, 2, 30, 0), (33, 1, 15, 1), (150, 1, 10, 0), (64, 3, 45, 1)])
+def test_sparse_bgp_matches_oracle(engine, N, D, Mz, kind):
+    pr = make_problem(N, D=D, n_genes=2, bs=(0.3, 0.7), seed=100 + N)
+    Z = _Z(Mz)
+    out = engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"], kernel=kind)
+    for k in range(pr["count"]):
+        b, h = pr["b"][k], pr["hyp"][k]
+        e, g = bgp_numpy.sparse_value_and_grad(pr["logPhi"][k], pr["Y"][pr["item_gene"][k]], pr["X"], Z, _pz(pr, b), b, h[0], h[1], h[2], kind)
+        assert out["status"][k] == 0
+        assert abs(out["elbo"][k] - e) <= ELBO_RTOL * abs(e), (out["elbo"][k], e)
+        assert relerr(out["grad_logPhi"][k], g["logPhi"]) <= GRAD_RTOL
+        scale = max(abs(g["ell"]), abs(g["var"]), abs(g["likvar"]))
+        for j, nm in enumerate(("ell", "var", "likvar")):
+            assert abs(out["grad_hyp"][k, j] - g[nm]) <= GRAD_RTOL * max(abs(g[nm]), 1e-3 * scale), (nm, out["grad_hyp"][k, j], g[nm])
+        assert abs(out["grad_b"][k, 0] - g["b"]) <= GRAD_RTOL * max(abs(g["b"]), 1e-3 * scale)
+
+
+def test_sparse_bound_only_and_waves(engine):
+    pr = make_problem(25, D=1, n_genes=2, bs=tuple(np.linspace(0.1, 0.9, 5)), seed=5)
+    Z = _Z(12)
+    a = engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"], want_grad=False)
+    engine.set_max_slots(3)
+    try:
+        b = engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"])
+    finally:
+        engine.set_max_slots(0)
+    assert np.allclose(a["elbo"], b["elbo"], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("N,D,nz", [(24, 3, 8), (40, 5, 20), (30, 2, 60)])
+def test_mbgp_multi_output_sparse_matches_oracle(engine, N, D, nz):
+    """MBGP _build_likelihood_sparse: per-output branching points and trunk masks on a shared logPhi; Mz = 3*nz (180 default)."""
+    pr = make_problem(N, D=D, seed=200 + N, mbgp=True)
+    t = pr["t"]
+    _, trunk = host_ref.init_logphi_mbgp(pr["phi0"], t)
+    eZ0 = host_ref.expand_prior_mbgp(pr["prior3"])
+    Zt = np.linspace(0, 1, nz, endpoint=False)
+    Z = np.array([[z, f] for z in Zt for f in (1, 2, 3)], dtype=float)
+    Bv = np.random.default_rng(N).uniform(0.1, 0.9, D)
+    h = np.array([[0.7, 1.3, 0.2]])
+    e, g = bgp_numpy.mbgp_sparse_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], Z, t, eZ0, trunk, Bv, h[0, 0], h[0, 1], h[0, 2])
+    out = engine.sparse_elbo_grad(t, Z, pr["Y"], pr["item_gene"][:1], Bv[None], pr["prior3"], h, pr["logPhi"][:1],
+                                  kernel=_lib.KERNEL_SQEXP, model=_lib.MODEL_MBGP, multi=True)
+    assert out["status"][0] == 0
+    assert abs(out["elbo"][0] - e) <= ELBO_RTOL * abs(e), (out["elbo"][0], e)
+    assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
+    assert relerr(out["grad_b"][0], g["Bv"]) <= GRAD_RTOL
+    assert np.allclose(out["grad_hyp"][0], [g["ell"], g["var"], g["likvar"]], rtol=GRAD_RTOL, atol=1e-6 * np.abs(out["grad_hyp"][0]).max())
