@@ -52,6 +52,14 @@ SIGNATURES = {
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_dense_predict_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_sparse_predict_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_void_p]),
     "bgp_get_phi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bgp_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
@@ -223,6 +231,44 @@ class Engine:
             raise CholeskyError(f"Cholesky decomposition was not successful for work item {i} (status {int(status[i])}): "
                                 "the input might not be valid")
         return dict(elbo=elbo, grad_hyp=grad_hyp, grad_b=grad_b, grad_logPhi=grad_logPhi, status=status)
+
+    # ------------------------------------------------------------------ predict_f
+    def dense_predict(self, t, Y, item_gene, b, prior, hyp, logPhi, Xnew, kernel=KERNEL_MATERN32, model=MODEL_BGP, full_cov=False):
+        """Posterior mean [count,T,D] and variance [count,T] (or [count,T,T]) of the latent functions at Xnew [T,2]."""
+        t = _f64(t)
+        Y = _f64(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        nY, N, D = Y.shape
+        item_gene = np.ascontiguousarray(item_gene, dtype=np.int32)
+        count = item_gene.size
+        b = _f64(b).reshape(count)
+        hyp = _f64(hyp).reshape(count, 3)
+        prior = _f64(prior)
+        logPhi = _f64(logPhi).reshape(count, N, 3 * N)
+        Xnew = _f64(Xnew)
+        T = Xnew.shape[0]
+        assert Xnew.shape == (T, 2)
+        mean = np.empty((count, T, D))
+        var = np.empty((count, T, T) if full_cov else (count, T))
+        rc = self._lib.bgp_dense_predict_host(self._h, count, N, D, _ptr(t), _ptr(Y), nY, _ptr(item_gene), _ptr(b), _ptr(prior),
+                                              _ptr(hyp), int(kernel), int(model), _ptr(logPhi), T, _ptr(Xnew), int(bool(full_cov)),
+                                              _ptr(mean), _ptr(var))
+        self._check(rc, "bgp_dense_predict_host")
+        return mean, var
+
+    def sparse_predict(self, t, Z, Y, b, prior, hyp, logPhi, Xnew, kernel=KERNEL_MATERN32, full_cov=False):
+        t, Z, Y, prior, Xnew = _f64(t), _f64(Z), _f64(Y), _f64(prior), _f64(Xnew)
+        N, D = Y.shape
+        hyp = _f64(hyp).reshape(3)
+        logPhi = _f64(logPhi).reshape(N, 3 * N)
+        T = Xnew.shape[0]
+        mean = np.empty((T, D))
+        var = np.empty((T, T) if full_cov else (T,))
+        rc = self._lib.bgp_sparse_predict_host(self._h, N, D, Z.shape[0], _ptr(t), _ptr(Z), _ptr(Y), float(b), _ptr(prior), _ptr(hyp),
+                                               int(kernel), _ptr(logPhi), T, _ptr(Xnew), int(bool(full_cov)), _ptr(mean), _ptr(var))
+        self._check(rc, "bgp_sparse_predict_host")
+        return mean, var
 
     def get_phi(self, logPhi):
         logPhi = _f64(logPhi)

@@ -197,5 +197,20 @@ class AssignGP:
             grads.append(-(g * p.transform.dforward(p.unconstrained_variable)))
         return loss, grads
 
+    def _hyp_row(self):
+        k = self._branch_kernel()
+        return np.array([[float(k.kern.lengthscales.numpy()), float(k.kern.variance.numpy()), float(self.likelihood.variance.numpy())]])
+
     def predict_f(self, Xnew, full_cov=False):
-        raise NotImplementedError("predict_f is the next row of the scope table (SURVEY.md 8f-f1); use FitModel(fPredict=False)")
+        """Posterior mean [T, D] and variance [T, D] (full_cov: [T, T, D]) at Xnew [T, 2] (assigngp_dense.py:201-240)."""
+        self._square_noise_ok()
+        if self.KConst is not None:
+            raise NotImplementedError("predict_f with KConst")
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        mean, var = self.engine.dense_predict(self.t, self.Y[None], np.zeros(1, dtype=np.int32), np.array([float(self.b.ravel()[0])]),
+                                              self._prior, self._hyp_row(), self.logPhi.numpy()[None], Xnew,
+                                              kernel=self._branch_kernel().kind, model=self.MODEL_KIND, full_cov=full_cov)
+        D = self.Y.shape[1]
+        if full_cov:
+            return mean[0], np.repeat(var[0][:, :, None], D, axis=2)
+        return mean[0], np.repeat(var[0][:, None], D, axis=1)

@@ -23,6 +23,8 @@ struct bgp_handle {
     size_t stage_bytes = 0;
     // description of the last dense wave, for the debug readers
     DenseParams lastP;
+    SparseParams lastS;        // parameters of the last sparse wave (device pointers into the staging area stay valid
+    bool keep_sparse = false;  //  until the next call), used by bgp_sparse_predict_host
     int last_slots = 0;
     bool kernels_ready = false;
     // optional per-kernel timing (bench.py): events recorded around every launch of a call
@@ -30,6 +32,8 @@ struct bgp_handle {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, int>> ev_marks;   // (phase id, index into ev_pool of the event recorded AFTER the launch)
     int ev_used = 0;
+    // set by bgp_dense_predict_host around a forward-only dense call
+    const double* pred_X = nullptr; int pred_T = 0; int pred_full = 0; double* pred_mean = nullptr; double* pred_var = nullptr;
     double prof_ms[BGP_NPHASES] = {0};
     long long launches = 0;
 };
@@ -73,7 +77,9 @@ static DenseDims make_dims(int N, int D) {
     d.nM = d.Mp / MB;
     d.D = D;
     d.nch = (N + PHI_RCH - 1) / PHI_RCH;
-    d.mat_elems = packed_tiles(d.nT) * TILE_ELEMS;
+    // PB / LB double as tall nT x 4 tile matrices in k_predict, which is larger than the packed triangle when nT < 7
+    const long long tiles = packed_tiles(d.nT) > 4LL * d.nT ? packed_tiles(d.nT) : 4LL * d.nT;
+    d.mat_elems = tiles * TILE_ELEMS;
     d.vec_elems = vec_layout(d.Mp, d.nM, D).total;
     return d;
 }
@@ -229,6 +235,15 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
             phi_launch_backward(F, n, st);
             prof_mark(h, 11, st);
         }
+        if (h->pred_T > 0) {   // predict_f on this wave's forward state, 128 test inputs per launch
+            const size_t vstride = h->pred_full ? (size_t)h->pred_T * h->pred_T : (size_t)h->pred_T;
+            for (int s0 = 0; s0 < h->pred_T; s0 += MB) {
+                const int tc = (h->pred_T - s0 < MB) ? (h->pred_T - s0) : MB;
+                dense_launch_predict(P, n, h->pred_X + 2 * (size_t)s0, tc, h->pred_T, s0, h->pred_full,
+                                     h->pred_mean + (size_t)item0 * h->pred_T * D, h->pred_var + (size_t)item0 * vstride, st);
+                h->launches++;
+            }
+        }
         CU(cudaGetLastError());
         h->last_slots = n;
     }
@@ -376,6 +391,7 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
         if (want_grad) { phi_launch_backward(F, n, st); h->launches++; }
         CU(cudaGetLastError());
     }
+    h->lastS = P;
     return BGP_OK;
 }
 
@@ -437,6 +453,71 @@ int bgp_sparse_elbo_grad_host(bgp_handle* h, int count, int N, int Dtot, int Mz,
     }
     h->max_slots = saved_slots;
     return rc;
+}
+
+// ---- predict_f ----------------------------------------------------------------------------------------------------
+int bgp_dense_predict_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY, const int* item_gene,
+                           const double* b, const double* prior, const double* hyp, int kernel_kind, int model,
+                           const double* logPhi, int T, const double* Xnew, int full_cov, double* mean, double* var) {
+    if (!h) return BGP_ERR_ARG;
+    if (T <= 0 || !Xnew || !mean || !var) return fail(h, BGP_ERR_ARG, "predict needs T > 0, Xnew, mean and var");
+    if (full_cov && T > MB) return fail(h, BGP_ERR_ARG, "full_cov is limited to %d test inputs per call", MB);
+    CU(cudaSetDevice(h->device));
+    const size_t vlen = full_cov ? (size_t)T * T : (size_t)T;
+    double *dX = nullptr, *dmean = nullptr, *dvar = nullptr, *delbo = nullptr;
+    int* dst = nullptr;
+    CU(cudaMalloc(&dX, (size_t)T * 16));
+    CU(cudaMalloc(&dmean, (size_t)count * T * D * 8));
+    CU(cudaMalloc(&dvar, (size_t)count * vlen * 8));
+    CU(cudaMemcpy(dX, Xnew, (size_t)T * 16, cudaMemcpyHostToDevice));
+    h->pred_X = dX; h->pred_T = T; h->pred_full = full_cov; h->pred_mean = dmean; h->pred_var = dvar;
+    const int saved = h->stop_phase;
+    h->stop_phase = 4;
+    std::vector<double> elbo(count);
+    std::vector<int> status(count);
+    int rc = bgp_dense_elbo_grad_host(h, count, N, D, t, Y, nY, item_gene, b, prior, hyp, kernel_kind, model, 1.0, logPhi, nullptr, 0,
+                                      elbo.data(), nullptr, nullptr, status.data());
+    h->stop_phase = saved;
+    h->pred_T = 0; h->pred_X = nullptr; h->pred_mean = nullptr; h->pred_var = nullptr;
+    if (rc == BGP_OK) {
+        cudaError_t e1 = cudaMemcpy(mean, dmean, (size_t)count * T * D * 8, cudaMemcpyDeviceToHost);
+        cudaError_t e2 = cudaMemcpy(var, dvar, (size_t)count * vlen * 8, cudaMemcpyDeviceToHost);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(h, BGP_ERR_CUDA, "predict copy back failed");
+        for (int i = 0; i < count && rc == BGP_OK; ++i)
+            if (status[i] != 0) rc = fail(h, BGP_ERR_CUDA, "Cholesky decomposition was not successful for item %d (status %d)", i, status[i]);
+    }
+    cudaFree(dX); cudaFree(dmean); cudaFree(dvar); (void)delbo; (void)dst;
+    return rc;
+}
+
+int bgp_sparse_predict_host(bgp_handle* h, int N, int Dtot, int Mz, const double* t, const double* Z, const double* Y, double b,
+                            const double* prior, const double* hyp, int kernel_kind, const double* logPhi, int T,
+                            const double* Xnew, int full_cov, double* mean, double* var) {
+    if (!h) return BGP_ERR_ARG;
+    if (T <= 0 || !Xnew || !mean || !var) return fail(h, BGP_ERR_ARG, "predict needs T > 0, Xnew, mean and var");
+    CU(cudaSetDevice(h->device));
+    // forward state of the single item: run the bound without gradient, then predict from the workspace of slot 0
+    double elbo = 0.0; int status = 0, gene = 0;
+    h->keep_sparse = true;
+    int rc = bgp_sparse_elbo_grad_host(h, 1, N, Dtot, Mz, t, Z, Y, 1, &gene, &b, prior, hyp, kernel_kind, BGP_MODEL_BGP, 0, logPhi, 0,
+                                       &elbo, nullptr, nullptr, nullptr, &status);
+    h->keep_sparse = false;
+    if (rc != BGP_OK) return rc;
+    if (status != 0) return fail(h, BGP_ERR_CUDA, "Cholesky decomposition was not successful (status %d)", status);
+    const size_t vlen = full_cov ? (size_t)T * T : (size_t)T;
+    double *dX = nullptr, *dscr = nullptr, *dmean = nullptr, *dvar = nullptr;
+    CU(cudaMalloc(&dX, (size_t)T * 16));
+    CU(cudaMalloc(&dscr, (size_t)3 * Mz * T * 8));
+    CU(cudaMalloc(&dmean, (size_t)T * Dtot * 8));
+    CU(cudaMalloc(&dvar, vlen * 8));
+    CU(cudaMemcpy(dX, Xnew, (size_t)T * 16, cudaMemcpyHostToDevice));
+    sparse_launch_predict(h->lastS, dX, T, full_cov, dscr, dmean, dvar, 0);
+    cudaError_t e0 = cudaGetLastError();
+    cudaError_t e1 = cudaMemcpy(mean, dmean, (size_t)T * Dtot * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e2 = cudaMemcpy(var, dvar, vlen * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dX); cudaFree(dscr); cudaFree(dmean); cudaFree(dvar);
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) return fail(h, BGP_ERR_CUDA, "sparse predict failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+    return BGP_OK;
 }
 
 int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi) {

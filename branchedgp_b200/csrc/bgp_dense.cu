@@ -675,6 +675,155 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_adj(DenseParams P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_predict
+// AssignGP.predict_f (assigngp_dense.py:201-240) for up to 128 test inputs per launch, after phases 1-4:
+//   tmp1 = (Lc + eps I)^-1 K(X, Xnew),  tmp2 = R^-1 tmp1,  mean = tmp2^T c,  var = Kdiag + colsum(tmp2^2) - colsum(tmp1^2)
+// tmp1 / tmp2 are tall tile matrices (nT x 4 tiles) kept in the PB / LB buffers, which the forward pass does not use.
+struct PredictArgs {
+    const double* Xnew;   // [T][2] (time, function 1..3)
+    int T;                // inputs in this launch, <= 128
+    int Ttot, s0;         // total number of test inputs of the call and offset of this launch (output row indexing)
+    int full_cov;         // only with Ttot <= 128
+    double* mean;         // [slot][T][D]
+    double* var;          // [slot][T] or [slot][T][T]
+};
+
+__device__ __forceinline__ double kpair(const DenseParams& P, double t1, int f1, double t2, int f2, double ell, double kvar, double kinv,
+                                        double b) {
+    if (f1 == f2) return kbase(t1 - t2, ell, kvar, P.kind);
+    return (kbase(t1 - b, ell, kvar, P.kind) * kinv) * kbase(t2 - b, ell, kvar, P.kind);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_predict(DenseParams P, PredictArgs Q) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    double* Dm = pipe.stages;
+    const int nM = dm.nM, nT = dm.nT, M = dm.M, T = Q.T, D = dm.D, Mp = dm.Mp;
+    const double b = P.bv[item];
+    const double kinv = 1.0 / (kvar + JITTER);
+    double* S0 = SCR;
+    double* S1 = SCR + 16 * TILE_ELEMS;
+    double* T1 = PB;   // tall tile matrices: tile (r, c) at (r*4 + c)
+    double* T2 = LB;
+    const Opnd opL = opnd_packed(LC, ACC_ROWK, LCe);
+    const Opnd opR = opnd_packed(RX, ACC_ROWK);
+    Acc acc;
+    for (int pass = 0; pass < 2; ++pass) {
+        double* Tout = pass == 0 ? T1 : T2;
+        const Opnd opMat = pass == 0 ? opL : opR;
+        const Opnd opPrev = opnd_block(Tout, ACC_COLK, 0, 0, 0);
+        for (int I = 0; I < nM; ++I) {
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opMat, TPM * I, opPrev, 0, 0, TPM * I, nullptr);
+            __syncthreads();
+            acc_foreach(acc, I, 0, [&](int it, int jt, int i, int j, double v0, double v1) {
+                const int a = it - TPM * I;
+                double s0, s1;
+                if (pass == 0) {
+                    const int gi = it * TS + i, s = jt * TS + j;
+                    s0 = s1 = 0.0;
+                    if (gi < M) {
+                        const int ci = gi / 3, fi = gi - 3 * ci + 1;
+                        if (s < T) s0 = kpair(P, P.t[ci], fi, Q.Xnew[2 * s], (int)Q.Xnew[2 * s + 1], ell, kvar, kinv, b);
+                        if (s + 1 < T) s1 = kpair(P, P.t[ci], fi, Q.Xnew[2 * s + 2], (int)Q.Xnew[2 * s + 3], ell, kvar, kinv, b);
+                    }
+                } else {
+                    const double2 p = tile_load2(T1 + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j);
+                    s0 = p.x; s1 = p.y;
+                }
+                tile_store2(S0 + (size_t)(a * TPM + jt) * TILE_ELEMS, i, j, s0 - v0, s1 - v1);
+            });
+            // inverse of the diagonal macro block: pass 0 needs inv(Lc_II + eps I) (computed here), pass 1 uses the stored inv(R_II)
+            const double* invblk;
+            if (pass == 0) {
+                __syncthreads();
+                for (int a = 0; a < TPM; ++a)
+                    for (int bb = 0; bb <= a; ++bb) {
+                        const double* src = (a == bb) ? LCe + (size_t)(TPM * I + a) * TILE_ELEMS : LC + packed_tile(TPM * I + a, TPM * I + bb) * TILE_ELEMS;
+                        for (int e = tid; e < TILE_ELEMS; e += NTHREADS) {
+                            const int i = e >> 5, j = e & 31;
+                            Dm[(TS * a + i) * DLD + TS * bb + j] = src[tswz(i, j)];
+                        }
+                    }
+                __syncthreads();
+                trinv128(Dm);
+                store_lower_block(Dm, I, nullptr, S1, nullptr, 0.0);
+                invblk = S1;
+            } else {
+                invblk = RinvD + (size_t)I * 16 * TILE_ELEMS;
+            }
+            fence_proxy_async();
+            __syncthreads();
+            acc_zero(acc);
+            gemm_macro(acc, pipe, opnd_block(invblk, ACC_ROWK, TPM * I, TPM * I, 1), TPM * I, opnd_block(S0, ACC_COLK, TPM * I, 0, 0), 0,
+                       TPM * I, TPM * I + TPM, nullptr);
+            acc_foreach(acc, I, 0, [&](int it, int jt, int i, int j, double v0, double v1) {
+                tile_store2(Tout + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j, v0, v1);
+            });
+            fence_proxy_async();
+            __syncthreads();
+        }
+    }
+    // mean and marginal variance: column reductions over the Mp rows
+    double* red = smem_red(smem);
+    {
+        const int s = tid & 127, half = tid >> 7;
+        const double* cv = vec + VL.c;
+        double sq = 0.0;
+        for (int d0 = 0; d0 < D; d0 += 1) {
+            double m = 0.0;
+            for (int i = half; i < Mp; i += 2) {
+                const double x2 = T2[(size_t)((i >> 5) * TPM + (s >> 5)) * TILE_ELEMS + tswz(i & 31, s & 31)];
+                m += x2 * cv[(size_t)d0 * Mp + i];
+                if (d0 == 0) {
+                    const double x1 = T1[(size_t)((i >> 5) * TPM + (s >> 5)) * TILE_ELEMS + tswz(i & 31, s & 31)];
+                    sq += x2 * x2 - x1 * x1;
+                }
+            }
+            __syncthreads();
+            red[tid] = m;
+            __syncthreads();
+            if (tid < 128 && s < T) Q.mean[((size_t)slot * Q.Ttot + Q.s0 + s) * D + d0] = red[tid] + red[tid + 128];
+        }
+        __syncthreads();
+        red[tid] = sq;
+        __syncthreads();
+        if (!Q.full_cov && tid < 128 && s < T) Q.var[(size_t)slot * Q.Ttot + Q.s0 + s] = kvar + P.square_noise + red[tid] + red[tid + 128];
+    }
+    if (Q.full_cov) {
+        // cov = K(Xnew) + tmp2^T tmp2 - tmp1^T tmp1   (128 x 128 Gram matrices through the tile GEMM)
+        const Opnd o2 = opnd_block(T2, ACC_COLK, 0, 0, 0), o1 = opnd_block(T1, ACC_COLK, 0, 0, 0);
+        acc_zero(acc);
+        gemm_macro(acc, pipe, o2, 0, o2, 0, 0, nT, nullptr);
+        acc_foreach(acc, 0, 0, [&](int it, int jt, int i, int j, double v0, double v1) {
+            tile_store2(S0 + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j, v0, v1);
+        });
+        acc_zero(acc);
+        gemm_macro(acc, pipe, o1, 0, o1, 0, 0, nT, nullptr);
+        acc_foreach(acc, 0, 0, [&](int it, int jt, int i, int j, double v0, double v1) {
+            const int s = it * TS + i, r = jt * TS + j;
+            const double2 g2 = tile_load2(S0 + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j);
+            if (s < T && r < T) {
+                double k = kpair(P, Q.Xnew[2 * s], (int)Q.Xnew[2 * s + 1], Q.Xnew[2 * r], (int)Q.Xnew[2 * r + 1], ell, kvar, kinv, b);
+                if (s == r) k += P.square_noise;
+                Q.var[((size_t)slot * T + s) * T + r] = k + g2.x - v0;
+            }
+            if (s < T && r + 1 < T) {
+                double k = kpair(P, Q.Xnew[2 * s], (int)Q.Xnew[2 * s + 1], Q.Xnew[2 * r + 2], (int)Q.Xnew[2 * r + 3], ell, kvar, kinv, b);
+                if (s == r + 1) k += P.square_noise;
+                Q.var[((size_t)slot * T + s) * T + r + 1] = k + g2.y - v1;
+            }
+        });
+    }
+}
+
+void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, int T, int Ttot, int s0, int full_cov, double* mean,
+                          double* var, cudaStream_t st) {
+    PredictArgs Q{Xnew, T, Ttot, s0, full_cov, mean, var};
+    k_predict<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P, Q);
+}
+
 // ------------------------------------------------------------------------------------------------ debug: unpack a tile matrix to row-major
 __global__ void k_unpack(const double* packed, double* out, int Mp, int symmetric) {
     const int nT = Mp / TS;
@@ -701,6 +850,7 @@ cudaError_t dense_init_kernels() {
     if ((e = set_smem((const void*)k_lauum)) != cudaSuccess) return e;
     if ((e = set_smem((const void*)k_trmm)) != cudaSuccess) return e;
     if ((e = set_smem((const void*)k_adj)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_predict)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -9,8 +9,12 @@ cudaError_t dense_init_kernels();
 void dense_launch_prep(const DenseParams& P, const double* Apart, const double* vpart, const double* klpart, const double* Y,
                        const int* item_gene, int nitems, cudaStream_t st);
 void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_t st);
+void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, int T, int Ttot, int s0, int full_cov, double* mean,
+                          double* var, cudaStream_t st);
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st);
 cudaError_t sparse_init_kernels();
 void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* sub_out, cudaStream_t st);
+void sparse_launch_predict(const SparseParams& P, const double* Xnew, int T, int full_cov, double* scratch, double* mean_out,
+                           double* var_out, cudaStream_t st);
 void phi_launch_gather(const double* logPhi, double* phi, int count, int N, cudaStream_t st);
 }  // namespace bgp

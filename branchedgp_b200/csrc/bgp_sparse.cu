@@ -508,6 +508,70 @@ __global__ void k_sp_reduce(SparseParams P, const double* sub_out, int nitems) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- k_sp_predict
+// AssignGPSparse.predict_f (assigngp_denseSparse.py:109-155) for one sub-problem whose forward state (Linv, Rinv, c) is in
+// the workspace.  scratch: 3 * Mz * T doubles.  Xnew[T][2] = (time, function).  full_cov: var_out is [T][T], else [T].
+__device__ __forceinline__ double k_pair(const SparseParams& P, double t1, int f1, double t2, int f2, double ell, double kvar,
+                                         double kinv, double bpt) {
+    if (f1 == f2) return kbase(t1 - t2, ell, kvar, P.kind);
+    return (kbase(t1 - bpt, ell, kvar, P.kind) * kinv) * kbase(t2 - bpt, ell, kvar, P.kind);
+}
+
+__global__ void __launch_bounds__(NTHREADS) k_sp_predict(SparseParams P, const double* Xnew, int T, int full_cov, double* scratch,
+                                                         double* mean_out, double* var_out) {
+    SP_SETUP();
+    double* Kus = scratch;
+    double* t1 = scratch + (size_t)Mz * T;
+    double* t2 = t1 + (size_t)Mz * T;
+    const double* Linv = ws + SLy.Linv;
+    const double* Rinv = ws + SLy.Rinv;
+    for (int e = tid; e < Mz * T; e += NTHREADS) {
+        const int m = e / T, s = e % T;
+        Kus[e] = k_pair(P, P.Z[2 * m], (int)P.Z[2 * m + 1], Xnew[2 * s], (int)Xnew[2 * s + 1], ell, kvar, kinv, bpt);
+    }
+    __syncthreads();
+    for (int e = tid; e < Mz * T; e += NTHREADS) {
+        const int m = e / T, s = e % T;
+        double a = 0.0;
+        for (int k = 0; k <= m; ++k) a += Linv[(size_t)m * Mz + k] * Kus[(size_t)k * T + s];
+        t1[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < Mz * T; e += NTHREADS) {
+        const int m = e / T, s = e % T;
+        double a = 0.0;
+        for (int k = 0; k <= m; ++k) a += Rinv[(size_t)m * Mz + k] * t1[(size_t)k * T + s];
+        t2[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < T * D; e += NTHREADS) {
+        const int s = e / D, d = e % D;
+        double a = 0.0;
+        for (int m = 0; m < Mz; ++m) a += t2[(size_t)m * T + s] * ws[SLy.c + (size_t)d * Mz + m];
+        mean_out[e] = a;
+    }
+    if (!full_cov) {
+        for (int s = tid; s < T; s += NTHREADS) {
+            double a = kvar + P.square_noise;
+            for (int m = 0; m < Mz; ++m) { const double x = t2[(size_t)m * T + s], y = t1[(size_t)m * T + s]; a += x * x - y * y; }
+            var_out[s] = a;
+        }
+    } else {
+        for (int e = tid; e < T * T; e += NTHREADS) {
+            const int s = e / T, r = e % T;
+            double a = k_pair(P, Xnew[2 * s], (int)Xnew[2 * s + 1], Xnew[2 * r], (int)Xnew[2 * r + 1], ell, kvar, kinv, bpt);
+            if (s == r) a += P.square_noise;
+            for (int m = 0; m < Mz; ++m) a += t2[(size_t)m * T + s] * t2[(size_t)m * T + r] - t1[(size_t)m * T + s] * t1[(size_t)m * T + r];
+            var_out[e] = a;
+        }
+    }
+}
+
+void sparse_launch_predict(const SparseParams& P, const double* Xnew, int T, int full_cov, double* scratch, double* mean_out,
+                           double* var_out, cudaStream_t st) {
+    k_sp_predict<<<dim3(1, 1), NTHREADS, 0, st>>>(P, Xnew, T, full_cov, scratch, mean_out, var_out);
+}
+
 // ---------------------------------------------------------------------------------------------------- launchers
 static size_t packed_bytes(int Mz) { return (size_t)Mz * (Mz + 1) / 2 * 8; }
 static size_t slab_bytes(int Mz, int nbuf) { return ((size_t)nbuf * Mz * (SP_SL + 1) + SP_SL) * 8; }

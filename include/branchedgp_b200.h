@@ -101,6 +101,17 @@ int bgp_sparse_elbo_grad_host(bgp_handle* h, int count, int N, int Dtot, int Mz,
                               const double* hyp, int kernel_kind, int model, int multi, const double* logPhi, int want_grad,
                               double* elbo, double* grad_hyp, double* grad_b, double* grad_logPhi, int* status);
 
+/* predict_f (assigngp_dense.py:201-240; MBGP/assigngp.py:560-647 per output): posterior mean[count][T][D] and marginal variance
+ * var[count][T] (full_cov: var[count][T][T], T <= 128) of the latent functions at Xnew[T][2] = (time, function in {1,2,3}).
+ * HOST pointers; same model arguments as bgp_dense_elbo_grad_host. */
+int bgp_dense_predict_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY, const int* item_gene,
+                           const double* b, const double* prior, const double* hyp, int kernel_kind, int model,
+                           const double* logPhi, int T, const double* Xnew, int full_cov, double* mean, double* var);
+/* AssignGPSparse.predict_f (assigngp_denseSparse.py:109-155), one model: mean[T][Dtot], var[T] or [T][T]. */
+int bgp_sparse_predict_host(bgp_handle* h, int N, int Dtot, int Mz, const double* t, const double* Z, const double* Y, double b,
+                            const double* prior, const double* hyp, int kernel_kind, const double* logPhi, int T,
+                            const double* Xnew, int full_cov, double* mean, double* var);
+
 /* AssignGP.GetPhi (assigngp_dense.py:130-140): softmax rows of logPhi gathered at the cell's own 3 columns -> Phi[count][N][3].
  * HOST pointers. */
 int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi);

@@ -270,3 +270,48 @@ def mbgp_dense_value_and_grad(logPhi, Y, X, t, eZ0, phiTrunk, Bv, ell, var, likv
     gb[0] = g.pop("b")
     g["Bv"] = gb
     return elbo, g
+
+
+# ------------------------------------------------------------------ predict_f (assigngp_dense.py:201-240, assigngp_denseSparse.py:109-155)
+def dense_predict(logPhi, Y, X, Xnew, b, ell, var, likvar, kind=MATERN32, square_noise=1e-6, full_cov=False, Phi_override=None):
+    M = X.shape[0]
+    s = likvar
+    Phi = SQ_A * softmax_rows(logPhi) + SQ_B if Phi_override is None else Phi_override
+    K = branch_K(X, X, b, ell, var, kind) + square_noise * np.eye(M)
+    L = cholesky(K, lower=True) + JITTER * np.eye(M)
+    A = Phi.sum(axis=0)
+    P = L.T @ ((A / s)[:, None] * L) + np.eye(M)
+    R = cholesky(P, lower=True)
+    c = solve_triangular(R, L.T @ (Phi.T @ Y), lower=True) / s
+    Kus = branch_K(X, Xnew, b, ell, var, kind)
+    tmp1 = solve_triangular(L, Kus, lower=True)
+    tmp2 = solve_triangular(R, tmp1, lower=True)
+    mean = tmp2.T @ c
+    if full_cov:
+        v = branch_K(Xnew, Xnew, b, ell, var, kind) + square_noise * np.eye(Xnew.shape[0]) + tmp2.T @ tmp2 - tmp1.T @ tmp1
+    else:
+        v = (var + square_noise) + (tmp2 ** 2).sum(0) - (tmp1 ** 2).sum(0)
+    return mean, v
+
+
+def sparse_predict(logPhi, Y, X, Z, Xnew, b, ell, var, likvar, kind=MATERN32, square_noise=1e-6, full_cov=False):
+    Mz = Z.shape[0]
+    s = likvar
+    Phi = SQ_A * softmax_rows(logPhi) + SQ_B
+    Kuu = branch_K(Z, Z, b, ell, var, kind) + (square_noise + JITTER) * np.eye(Mz)
+    Kuf = branch_K(Z, X, b, ell, var, kind)
+    L = cholesky(Kuu, lower=True)
+    A = Phi.sum(axis=0)
+    V = solve_triangular(L, Kuf, lower=True)
+    P = (V * (A / s)[None, :]) @ V.T + np.eye(Mz)
+    R = cholesky(P, lower=True)
+    c = solve_triangular(R, V @ (Phi.T @ Y), lower=True) / s
+    Kus = branch_K(Z, Xnew, b, ell, var, kind)
+    tmp1 = solve_triangular(L, Kus, lower=True)
+    tmp2 = solve_triangular(R, tmp1, lower=True)
+    mean = tmp2.T @ c
+    if full_cov:
+        v = branch_K(Xnew, Xnew, b, ell, var, kind) + square_noise * np.eye(Xnew.shape[0]) + tmp2.T @ tmp2 - tmp1.T @ tmp1
+    else:
+        v = (var + square_noise) + (tmp2 ** 2).sum(0) - (tmp1 ** 2).sum(0)
+    return mean, v
