@@ -14,7 +14,7 @@ KERNEL_SQEXP = 1
 MODEL_BGP = 0
 MODEL_MBGP = 1
 
-_LIB_NAME = "libbgp_b200.so"
+_LIB_NAME = os.environ.get("BGP_LIB_NAME", "libbgp_b200.so")   # test hook: alternative builds of the same library
 _lib = None
 _lib_lock = threading.Lock()
 

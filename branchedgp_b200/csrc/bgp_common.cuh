@@ -23,7 +23,7 @@ constexpr int STAGE_BYTES = STAGE_ELEMS * 8;          // 64 KB
 constexpr int PIPE_BYTES = NSTAGES * STAGE_BYTES;     // 192 KB
 constexpr int DLD = MB + 1;                           // padded leading dimension of the 128x128 smem scratch
 constexpr int SMEM_RED_DOUBLES = 3 * NTHREADS;
-constexpr int SMEM_BYTES = PIPE_BYTES + SMEM_RED_DOUBLES * 8 + 64;   // + reduction scratch + mbarriers
+constexpr int SMEM_BYTES = PIPE_BYTES + SMEM_RED_DOUBLES * 8 + 64;   // + reduction scratch + 2*NSTAGES mbarriers
 
 constexpr double JITTER = 1e-6;        // gpflow.default_jitter()
 constexpr double SQ_A = 1.0 - 2e-6;    // assigngp_dense.py:162
@@ -43,6 +43,9 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -69,7 +72,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 
 // D(8x8) += A(8x4, row) * B(4x8, col).  lane = 4*g + c:  a = A[g][c],  b = B[c][g],  d = {D[g][2c], D[g][2c+1]}.
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d0), "+d"(d1)
         : "d"(a), "d"(b));
 }

@@ -10,7 +10,13 @@
 #pragma once
 #include "bgp_common.cuh"
 
+#ifndef BGP_KUNROLL
+#define BGP_KUNROLL 2
+#endif
+
 namespace bgp {
+
+constexpr int KUNROLL = BGP_KUNROLL;   // unroll factor of the k4 loop of warp_kstep
 
 enum { ACC_ROWK = 0, ACC_COLK = 1, ACC_SYM = 2 };
 enum { LAY_PACKED = 0, LAY_BLOCK = 1 };
@@ -52,16 +58,18 @@ __device__ __forceinline__ const double* resolve(const Opnd& op, int o, int kt, 
 
 struct Pipe {
     double* stages;    // NSTAGES * STAGE_ELEMS doubles of shared memory
-    uint64_t* full;    // NSTAGES mbarriers
+    uint64_t* full;    // NSTAGES mbarriers: TMA bytes of the stage have landed
+    uint64_t* empty;   // NSTAGES mbarriers: all 8 warps are done reading the stage
     uint32_t it;       // running k-step counter; identical in every thread of the CTA
 };
 
 __device__ __forceinline__ void pipe_init(Pipe& p, unsigned char* smem) {
     p.stages = reinterpret_cast<double*>(smem);
     p.full = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES + SMEM_RED_DOUBLES * 8);
+    p.empty = p.full + NSTAGES;
     p.it = 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGES; ++s) mbar_init(p.full + s, 1);
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(p.full + s, 1); mbar_init(p.empty + s, NTHREADS / 32); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -77,8 +85,10 @@ __device__ __forceinline__ void acc_zero(Acc& acc) {
         for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 }
 
-// One 32-wide k-step of the warp tile.  nmask bit h enables the h-th 32-column half of the warp's 64 columns.
-template <bool TA, bool TB>
+// One 32-wide k-step of the warp tile.  FULL: both 32-column halves of the warp's 64 columns are live (no predication);
+// otherwise nmask bit h enables half h.  The k4 loop is only partially unrolled so that the body stays inside the L0
+// instruction cache (ncu: a fully unrolled body cost ~10 % of issue slots in no_instruction stalls).
+template <bool TA, bool TB, bool FULL>
 __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ As, const double* __restrict__ Bs0,
                                            const double* __restrict__ Bs1, int nmask, const double* __restrict__ ksc,
                                            int g, int c) {
@@ -89,15 +99,16 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
     //   transposed      tile[4*k4+c][8*o8+g]  ->  (4*k4+c)*32 + ((8*o8+g) ^ c2)
     const int nbase = g * TS + c;
     const int tbase = c * TS;
+    int toff[4];
 #pragma unroll
+    for (int o8 = 0; o8 < 4; ++o8) toff[o8] = tbase + ((8 * o8 + g) ^ c2);
+    const bool h0 = FULL || (nmask & 1), h1 = FULL || (nmask & 2);
+#pragma unroll KUNROLL
     for (int k4 = 0; k4 < 8; ++k4) {
         double af[4], bf[8];
         const int kx = ((4 * k4) ^ g3);
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const int off = TA ? (tbase + 4 * k4 * TS + ((8 * mi + g) ^ c2)) : (nbase + 8 * mi * TS + kx);
-            af[mi] = As[off];
-        }
+        for (int mi = 0; mi < 4; ++mi) af[mi] = As[TA ? (toff[mi] + 4 * k4 * TS) : (nbase + 8 * mi * TS + kx)];
         if (ksc != nullptr) {
             const double s = ksc[4 * k4 + c];
 #pragma unroll
@@ -107,22 +118,30 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
         for (int ni = 0; ni < 8; ++ni) {
             const int o8 = ni & 3;
             const double* Bt = (ni >> 2) ? Bs1 : Bs0;
-            const int off = TB ? (tbase + 4 * k4 * TS + ((8 * o8 + g) ^ c2)) : (nbase + 8 * o8 * TS + kx);
-            bf[ni] = (nmask & (1 << (ni >> 2))) ? Bt[off] : 0.0;
+            const int off = TB ? (toff[o8] + 4 * k4 * TS) : (nbase + 8 * o8 * TS + kx);
+            if (FULL) bf[ni] = Bt[off];
+            else bf[ni] = ((ni >> 2) ? h1 : h0) ? Bt[off] : 0.0;
         }
-        if (nmask & 1) {
+        if (h0) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
-        if (nmask & 2) {
+        if (h1) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 4; ni < 8; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
     }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void warp_kstep_dispatch(Acc& acc, bool ta, bool tb, const double* As, const double* Bs0, const double* Bs1,
+                                                    int nmask, const double* ksc, int g, int c) {
+    if (ta) { if (tb) warp_kstep<true, true, FULL>(acc, As, Bs0, Bs1, nmask, ksc, g, c); else warp_kstep<true, false, FULL>(acc, As, Bs0, Bs1, nmask, ksc, g, c); }
+    else    { if (tb) warp_kstep<false, true, FULL>(acc, As, Bs0, Bs1, nmask, ksc, g, c); else warp_kstep<false, false, FULL>(acc, As, Bs0, Bs1, nmask, ksc, g, c); }
 }
 
 // acc += Aop[ao0*32 .. +128][kt0*32 .. kt1*32) * Bop[bo0*32 .. +128][same k]^T, optionally with the k index scaled
@@ -157,12 +176,19 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
     __syncthreads();   // every warp is done with the ring (previous GEMM or scratch use)
     if (tid == 0) {
         const int pre = nk < (NSTAGES - 1) ? nk : (NSTAGES - 1);
-        for (int p = 0; p < pre; ++p) issue(p);
+        for (int p = 0; p < pre; ++p) {
+            const uint32_t itn = pipe.it + (uint32_t)p;
+            if (itn >= NSTAGES) mbar_wait(pipe.empty + itn % NSTAGES, ((itn / NSTAGES) - 1u) & 1u);
+            issue(p);
+        }
     }
     for (int ks = 0; ks < nk; ++ks) {
         if (ks + NSTAGES - 1 < nk) {
-            __syncthreads();   // slot (ks-1)%NSTAGES has been consumed by every warp
-            if (tid == 0) issue(ks + NSTAGES - 1);
+            if (tid == 0) {   // refill the slot released NSTAGES-1 k-steps ago once all 8 warps have arrived on its `empty` barrier
+                const uint32_t itn = pipe.it + (uint32_t)(ks + NSTAGES - 1);
+                if (itn >= NSTAGES) mbar_wait(pipe.empty + itn % NSTAGES, ((itn / NSTAGES) - 1u) & 1u);
+                issue(ks + NSTAGES - 1);
+            }
         }
         const uint32_t it = pipe.it + (uint32_t)ks;
         const int st = (int)(it % NSTAGES);
@@ -172,22 +198,22 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
         const double* pa = resolve(A, ao0 + wa, kt, ta);
         const double* pb0 = resolve(B, bo0 + wb, kt, tb0);
         const double* pb1 = resolve(B, bo0 + wb + 1, kt, tb1);
-        if (pa == nullptr) continue;
+        if (pa == nullptr) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
         int nmask = (pb0 != nullptr ? 1 : 0) | (pb1 != nullptr ? 2 : 0);
-        if (nmask == 0) continue;
+        if (nmask == 0) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
         const double* sb = pipe.stages + (size_t)st * STAGE_ELEMS;
         const double* As = sb + (size_t)wa * TILE_ELEMS;
         const double* Bs0 = sb + (size_t)(4 + wb) * TILE_ELEMS;
         const double* Bs1 = Bs0 + TILE_ELEMS;
         const double* ksc = kscale ? kscale + (size_t)kt * TS : nullptr;
-        if (nmask == 3 && tb0 != tb1) {   // the two column halves need different orientations (SYM operand crossing its diagonal)
-            if (ta) { if (tb0) warp_kstep<true, true>(acc, As, Bs0, Bs1, 1, ksc, g, c); else warp_kstep<true, false>(acc, As, Bs0, Bs1, 1, ksc, g, c); }
-            else    { if (tb0) warp_kstep<false, true>(acc, As, Bs0, Bs1, 1, ksc, g, c); else warp_kstep<false, false>(acc, As, Bs0, Bs1, 1, ksc, g, c); }
-            nmask = 2;
+        if (nmask == 3 && tb0 == tb1) {
+            warp_kstep_dispatch<true>(acc, ta, tb0, As, Bs0, Bs1, 3, ksc, g, c);
+        } else {
+            if (nmask & 1) warp_kstep_dispatch<false>(acc, ta, tb0, As, Bs0, Bs1, 1, ksc, g, c);
+            if (nmask & 2) warp_kstep_dispatch<false>(acc, ta, tb1, As, Bs0, Bs1, 2, ksc, g, c);
         }
-        const bool tb = (nmask & 1) ? tb0 : tb1;
-        if (ta) { if (tb) warp_kstep<true, true>(acc, As, Bs0, Bs1, nmask, ksc, g, c); else warp_kstep<true, false>(acc, As, Bs0, Bs1, nmask, ksc, g, c); }
-        else    { if (tb) warp_kstep<false, true>(acc, As, Bs0, Bs1, nmask, ksc, g, c); else warp_kstep<false, false>(acc, As, Bs0, Bs1, nmask, ksc, g, c); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pipe.empty + st);
     }
     pipe.it += (uint32_t)nk;
 }

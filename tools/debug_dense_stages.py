@@ -39,7 +39,7 @@ def main(N=50, D=1, kind=0):
     print("Lc    ", relerr(LC, pad(st["Lc"], True)))
     run(2)
     P = eng.debug_matrix(N, 0, 1)
-    print("P     ", relerr(P, np.tril(pad(st["P"], True))))
+    print("P     ", relerr(np.tril(P), np.tril(pad(st["P"], True))))
     run(3)
     R = eng.debug_matrix(N, 0, 1)
     print("R     ", relerr(R, pad(st["R"], True)))
