@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=1000, help="N (C2 = 1000)")
     ap.add_argument("--items", type=int, default=296, help="work items per step per GPU")
-    ap.add_argument("--e2e-items", type=int, default=148)
+    ap.add_argument("--e2e-items", type=int, default=296)
     ap.add_argument("--ref-items", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")

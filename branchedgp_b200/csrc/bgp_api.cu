@@ -27,6 +27,10 @@ struct bgp_handle {
     bool keep_sparse = false;  //  until the next call), used by bgp_sparse_predict_host
     int last_slots = 0;
     bool kernels_ready = false;
+    std::vector<cudaStream_t> lane_streams;   // streams of the host-pointer entry points (one per in-flight item group)
+    cudaEvent_t shared_ready = nullptr;
+    void* pin = nullptr;       // pinned host scratch for the small per-item results of the host-pointer entry points
+    size_t pin_bytes = 0;
     // optional per-kernel timing (bench.py): events recorded around every launch of a call
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -129,6 +133,9 @@ int bgp_destroy(bgp_handle* h) {
     if (!h) return BGP_OK;
     cudaSetDevice(h->device);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaStream_t s_ : h->lane_streams) cudaStreamDestroy(s_);
+    if (h->shared_ready) cudaEventDestroy(h->shared_ready);
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
     delete h;
@@ -168,25 +175,14 @@ static int pick_slots(bgp_handle* h, int count, size_t slot_bytes) {
     return cap;
 }
 
-int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
-                        const int* item_gene, const double* b, const double* prior, const double* hyp, int kernel_kind,
-                        int model, double kl_weight, const double* logPhi, const double* KConst, int want_grad,
-                        double* elbo, double* grad_hyp, double* grad_logPhi, int* status, void* cuda_stream) {
-    if (!h) return BGP_ERR_ARG;
-    if (count <= 0 || N <= 0 || D <= 0 || nY <= 0) return fail(h, BGP_ERR_ARG, "count, N, D, nY must be positive");
-    if (!t || !Y || !item_gene || !b || !prior || !hyp || !logPhi || !elbo || !status) return fail(h, BGP_ERR_ARG, "null input pointer");
-    if (want_grad && (!grad_hyp || !grad_logPhi)) return fail(h, BGP_ERR_ARG, "want_grad needs grad_hyp and grad_logPhi");
-    if (kernel_kind != BGP_KERNEL_MATERN32 && kernel_kind != BGP_KERNEL_SQEXP) return fail(h, BGP_ERR_ARG, "unknown kernel kind %d", kernel_kind);
-    if (model != BGP_MODEL_BGP && model != BGP_MODEL_MBGP) return fail(h, BGP_ERR_ARG, "unknown model %d", model);
-    CU(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream;
+// One call's worth of waves on `st`, using `slots` workspace slots starting at `base`.  `global_item0` is the index of the
+// call's first item in caller-global arrays that are not staged per call (the predict outputs).
+static int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, const int* item_gene, const double* b,
+                     const double* prior, const double* hyp, int kernel_kind, int model, double kl_weight, const double* logPhi,
+                     const double* KConst, int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status,
+                     char* base, int slots, cudaStream_t st, bool mark, int global_item0) {
     const DenseDims d = make_dims(N, D);
     const SlotLayout SL = slot_layout(d);
-    const int slots = pick_slots(h, count, SL.total);
-    if (slots < 1) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d needs %zu bytes of workspace", N, SL.total);
-    int rc = ensure_ws(h, (size_t)slots * SL.total);
-    if (rc != BGP_OK) return rc;
-    char* base = (char*)h->ws;
     const size_t stride_d = SL.total / 8;   // slot stride in doubles (SL.total is a multiple of 256)
 
     DenseParams P;
@@ -215,32 +211,34 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
     F.Abar = P.vec + VL.Abar; F.vbar = P.vec + VL.vbar;
     F.grad_logPhi = grad_logPhi;
 
+    auto pm = [&](int phase) { if (mark) prof_mark(h, phase, st); else if (phase >= 0) h->launches++; };
     for (int item0 = 0; item0 < count; item0 += slots) {
         const int n = (count - item0 < slots) ? (count - item0) : slots;
         P.item0 = item0;
         F.item0 = item0;
         const int last = h->stop_phase > 0 ? h->stop_phase : 99;
-        prof_mark(h, -1, st);
+        pm(-1);
         phi_launch_forward(F, n, st);
-        prof_mark(h, 0, st);
+        pm(0);
         dense_launch_prep(P, F.Apart, F.vpart, F.klpart, Y, item_gene, n, st);
-        prof_mark(h, 1, st);
+        pm(1);
         for (int phase = 1; phase <= 9 && phase <= last; ++phase) {
             const bool grad_phase = (phase == 5 || phase == 6 || phase == 7 || phase == 9);
             if (grad_phase && !want_grad) continue;
             dense_launch_phase(P, n, phase, st);
-            prof_mark(h, phase + 1, st);
+            pm(phase + 1);
         }
         if (want_grad && last >= 9) {
             phi_launch_backward(F, n, st);
-            prof_mark(h, 11, st);
+            pm(11);
         }
         if (h->pred_T > 0) {   // predict_f on this wave's forward state, 128 test inputs per launch
             const size_t vstride = h->pred_full ? (size_t)h->pred_T * h->pred_T : (size_t)h->pred_T;
+            const size_t g0 = (size_t)global_item0 + item0;
             for (int s0 = 0; s0 < h->pred_T; s0 += MB) {
                 const int tc = (h->pred_T - s0 < MB) ? (h->pred_T - s0) : MB;
                 dense_launch_predict(P, n, h->pred_X + 2 * (size_t)s0, tc, h->pred_T, s0, h->pred_full,
-                                     h->pred_mean + (size_t)item0 * h->pred_T * D, h->pred_var + (size_t)item0 * vstride, st);
+                                     h->pred_mean + g0 * h->pred_T * D, h->pred_var + g0 * vstride, st);
                 h->launches++;
             }
         }
@@ -249,6 +247,35 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
     }
     h->lastP = P;
     return BGP_OK;
+}
+
+static int dense_check_args(bgp_handle* h, int count, int N, int D, int nY, const void* t, const void* Y, const void* item_gene,
+                            const void* b, const void* prior, const void* hyp, int kernel_kind, int model, const void* logPhi,
+                            int want_grad, const void* elbo, const void* grad_hyp, const void* grad_logPhi, const void* status) {
+    if (count <= 0 || N <= 0 || D <= 0 || nY <= 0) return fail(h, BGP_ERR_ARG, "count, N, D, nY must be positive");
+    if (!t || !Y || !item_gene || !b || !prior || !hyp || !logPhi || !elbo || !status) return fail(h, BGP_ERR_ARG, "null input pointer");
+    if (want_grad && (!grad_hyp || !grad_logPhi)) return fail(h, BGP_ERR_ARG, "want_grad needs grad_hyp and grad_logPhi");
+    if (kernel_kind != BGP_KERNEL_MATERN32 && kernel_kind != BGP_KERNEL_SQEXP) return fail(h, BGP_ERR_ARG, "unknown kernel kind %d", kernel_kind);
+    if (model != BGP_MODEL_BGP && model != BGP_MODEL_MBGP) return fail(h, BGP_ERR_ARG, "unknown model %d", model);
+    return BGP_OK;
+}
+
+int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
+                        const int* item_gene, const double* b, const double* prior, const double* hyp, int kernel_kind,
+                        int model, double kl_weight, const double* logPhi, const double* KConst, int want_grad,
+                        double* elbo, double* grad_hyp, double* grad_logPhi, int* status, void* cuda_stream) {
+    if (!h) return BGP_ERR_ARG;
+    int rc = dense_check_args(h, count, N, D, nY, t, Y, item_gene, b, prior, hyp, kernel_kind, model, logPhi, want_grad, elbo, grad_hyp,
+                              grad_logPhi, status);
+    if (rc != BGP_OK) return rc;
+    CU(cudaSetDevice(h->device));
+    const SlotLayout SL = slot_layout(make_dims(N, D));
+    const int slots = pick_slots(h, count, SL.total);
+    if (slots < 1) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d needs %zu bytes of workspace", N, SL.total);
+    rc = ensure_ws(h, (size_t)slots * SL.total);
+    if (rc != BGP_OK) return rc;
+    return dense_run(h, count, N, D, t, Y, item_gene, b, prior, hyp, kernel_kind, model, kl_weight, logPhi, KConst, want_grad, elbo,
+                     grad_hyp, grad_logPhi, status, (char*)h->ws, slots, (cudaStream_t)cuda_stream, true, 0);
 }
 
 // ---- host-pointer variant ---------------------------------------------------------------------------------------
@@ -261,65 +288,125 @@ static int ensure_stage(bgp_handle* h, size_t bytes) {
     return BGP_OK;
 }
 
+// Host-pointer entry.  The items are cut into groups of about a quarter of the SMs; each group owns a lane (CUDA stream +
+// workspace slots + staging buffers) on which its H2D copy, kernels and D2H copy are queued in order.  Up to four groups
+// compute concurrently (their one-CTA-per-item kernels share the SMs) while the copy engines move the next / previous
+// groups, so for calls with more than one SM-count of items the PCIe time hides behind the arithmetic.
 int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
                              const int* item_gene, const double* b, const double* prior, const double* hyp,
                              int kernel_kind, int model, double kl_weight, const double* logPhi, const double* KConst,
                              int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status) {
     if (!h) return BGP_ERR_ARG;
-    if (count <= 0 || N <= 0 || D <= 0 || nY <= 0) return fail(h, BGP_ERR_ARG, "count, N, D, nY must be positive");
+    int rc = dense_check_args(h, count, N, D, nY, t, Y, item_gene, b, prior, hyp, kernel_kind, model, logPhi, want_grad, elbo, grad_hyp,
+                              grad_logPhi, status);
+    if (rc != BGP_OK) return rc;
     CU(cudaSetDevice(h->device));
     const size_t M = 3 * (size_t)N;
     const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
-    // work in chunks so that the staged logPhi / gradient stay bounded
-    const DenseDims d = make_dims(N, D);
-    const SlotLayout SL = slot_layout(d);
+    const SlotLayout SL = slot_layout(make_dims(N, D));
     const size_t per_item = (size_t)N * M * 8;
+    const int conc = 4;
+    int sm_cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
+    if (sm_cap > count) sm_cap = count;
+    int gs = (sm_cap + conc - 1) / conc;                 // items per group
+    if (gs < 1) gs = 1;
+    int ngroups = (count + gs - 1) / gs;
+    int lanes = ngroups < 2 * conc ? ngroups : 2 * conc;
+    // per-lane staging: per-item inputs, outputs, logPhi and gradient
+    size_t lo = 0;
+    auto ltake = [&](size_t bytes) { size_t r = lo; lo = align_up(lo + bytes, 256); return r; };
+    size_t l_gene, l_b, l_hyp, l_elbo, l_gh, l_st, l_lp, l_g;
+    auto lane_layout = [&]() {
+        lo = 0;
+        l_gene = ltake((size_t)gs * 4); l_b = ltake((size_t)gs * 8); l_hyp = ltake((size_t)gs * 24);
+        l_elbo = ltake((size_t)gs * 8); l_gh = ltake((size_t)gs * 32); l_st = ltake((size_t)gs * 4);
+        l_lp = ltake((size_t)gs * per_item); l_g = ltake(want_grad ? (size_t)gs * per_item : 0);
+    };
+    lane_layout();
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const size_t avail = free_b + h->ws_bytes + h->stage_bytes;
-    int cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
-    const size_t per_slot_all = SL.total + 2 * per_item;
-    if ((size_t)cap * per_slot_all > (size_t)(0.85 * (double)avail)) cap = (int)((size_t)(0.85 * (double)avail) / per_slot_all);
-    if (cap < 1) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d does not fit in device memory", N);
-    if (cap > count) cap = count;
-    const int saved_slots = h->max_slots;
-    h->max_slots = cap;
-
+    const size_t avail = (size_t)(0.85 * (double)(free_b + h->ws_bytes + h->stage_bytes));
+    while (lanes > 1 && (size_t)lanes * ((size_t)gs * SL.total + lo) > avail) --lanes;
+    while (gs > 1 && (size_t)lanes * ((size_t)gs * SL.total + lo) > avail) { gs = (gs + 1) / 2; lane_layout(); }
+    if ((size_t)lanes * ((size_t)gs * SL.total + lo) > avail) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d does not fit in device memory", N);
+    ngroups = (count + gs - 1) / gs;
+    rc = ensure_ws(h, (size_t)lanes * gs * SL.total);
+    if (rc != BGP_OK) return rc;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     const size_t o_t = take((size_t)N * 8), o_Y = take((size_t)nY * N * D * 8), o_prior = take((size_t)N * pcols * 8);
     const size_t o_K = take(KConst ? M * M * 8 : 0);
-    const size_t o_gene = take((size_t)cap * 4), o_b = take((size_t)cap * 8), o_hyp = take((size_t)cap * 24);
-    const size_t o_elbo = take((size_t)cap * 8), o_gh = take((size_t)cap * 32), o_st = take((size_t)cap * 4);
-    const size_t o_lp = take((size_t)cap * per_item), o_g = take(want_grad ? (size_t)cap * per_item : 0);
-    int rc = ensure_stage(h, o);
-    if (rc != BGP_OK) { h->max_slots = saved_slots; return rc; }
-    char* s = (char*)h->stage;
-    cudaStream_t st = 0;
-    CU(cudaMemcpyAsync(s + o_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s + o_Y, Y, (size_t)nY * N * D * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s + o_prior, prior, (size_t)N * pcols * 8, cudaMemcpyHostToDevice, st));
-    if (KConst) CU(cudaMemcpyAsync(s + o_K, KConst, M * M * 8, cudaMemcpyHostToDevice, st));
-    for (int i0 = 0; i0 < count && rc == BGP_OK; i0 += cap) {
-        const int n = (count - i0 < cap) ? (count - i0) : cap;
-        CU(cudaMemcpyAsync(s + o_gene, item_gene + i0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s + o_b, b + i0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s + o_hyp, hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s + o_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, st));
-        rc = bgp_dense_elbo_grad(h, n, N, D, (double*)(s + o_t), (double*)(s + o_Y), nY, (int*)(s + o_gene), (double*)(s + o_b),
-                                 (double*)(s + o_prior), (double*)(s + o_hyp), kernel_kind, model, kl_weight, (double*)(s + o_lp),
-                                 KConst ? (double*)(s + o_K) : nullptr, want_grad, (double*)(s + o_elbo), (double*)(s + o_gh),
-                                 want_grad ? (double*)(s + o_g) : nullptr, (int*)(s + o_st), st);
-        if (rc != BGP_OK) break;
-        CU(cudaMemcpyAsync(elbo + i0, s + o_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(status + i0, s + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (want_grad) {
-            CU(cudaMemcpyAsync(grad_hyp + (size_t)i0 * 4, s + o_gh, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, s + o_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
-        }
-        CU(cudaStreamSynchronize(st));
+    const size_t o_lanes = take((size_t)lanes * lo);
+    rc = ensure_stage(h, o);
+    if (rc != BGP_OK) return rc;
+    while ((int)h->lane_streams.size() < lanes) {
+        // earlier lanes get higher priority so that groups complete roughly in order (their D2H then overlaps later groups)
+        int lo_p = 0, hi_p = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));   // hi_p is numerically the smallest
+        int prio = hi_p + (int)h->lane_streams.size();
+        if (prio > lo_p) prio = lo_p;
+        cudaStream_t s_;
+        CU(cudaStreamCreateWithPriority(&s_, cudaStreamNonBlocking, prio));
+        h->lane_streams.push_back(s_);
     }
-    h->max_slots = saved_slots;
+    if (!h->shared_ready) CU(cudaEventCreateWithFlags(&h->shared_ready, cudaEventDisableTiming));
+    // small results land in pinned scratch (an async copy into pageable memory would block the host until the group is done)
+    const size_t pin_need = (size_t)count * 48 + (size_t)count * 40;
+    if (h->pin_bytes < pin_need) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr; h->pin_bytes = 0;
+        CU(cudaHostAlloc(&h->pin, pin_need, cudaHostAllocDefault));
+        h->pin_bytes = pin_need;
+    }
+    double* pin_elbo = (double*)h->pin;
+    double* pin_gh = pin_elbo + count;
+    int* pin_st = (int*)(pin_gh + (size_t)4 * count);
+    // ... and so do the small per-item inputs (an async copy from pageable memory synchronises with the stream first)
+    double* pin_b = (double*)((char*)h->pin + (size_t)count * 48);
+    double* pin_hyp = pin_b + count;
+    int* pin_gene = (int*)(pin_hyp + (size_t)3 * count);
+    memcpy(pin_b, b, (size_t)count * 8);
+    memcpy(pin_hyp, hyp, (size_t)count * 24);
+    memcpy(pin_gene, item_gene, (size_t)count * 4);
+    char* s = (char*)h->stage;
+    cudaStream_t s0 = h->lane_streams[0];
+    CU(cudaMemcpyAsync(s + o_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(s + o_Y, Y, (size_t)nY * N * D * 8, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(s + o_prior, prior, (size_t)N * pcols * 8, cudaMemcpyHostToDevice, s0));
+    if (KConst) CU(cudaMemcpyAsync(s + o_K, KConst, M * M * 8, cudaMemcpyHostToDevice, s0));
+    CU(cudaEventRecord(h->shared_ready, s0));
+    for (int l = 1; l < lanes; ++l) CU(cudaStreamWaitEvent(h->lane_streams[l], h->shared_ready, 0));
+    for (int g = 0; g < ngroups && rc == BGP_OK; ++g) {
+        const int l = g % lanes;
+        cudaStream_t st = h->lane_streams[l];
+        const int i0 = g * gs;
+        const int n = (count - i0 < gs) ? (count - i0) : gs;
+        char* ls = s + o_lanes + (size_t)l * lo;
+        CU(cudaMemcpyAsync(ls + l_gene, pin_gene + i0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ls + l_b, pin_b + i0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ls + l_hyp, pin_hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ls + l_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, st));
+        rc = dense_run(h, n, N, D, (double*)(s + o_t), (double*)(s + o_Y), (int*)(ls + l_gene), (double*)(ls + l_b), (double*)(s + o_prior),
+                       (double*)(ls + l_hyp), kernel_kind, model, kl_weight, (double*)(ls + l_lp), KConst ? (double*)(s + o_K) : nullptr,
+                       want_grad, (double*)(ls + l_elbo), (double*)(ls + l_gh), want_grad ? (double*)(ls + l_g) : nullptr,
+                       (int*)(ls + l_st), (char*)h->ws + (size_t)l * gs * SL.total, gs, st, false, i0);
+        if (rc != BGP_OK) break;
+        CU(cudaMemcpyAsync(pin_elbo + i0, ls + l_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(pin_st + i0, ls + l_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (want_grad) {
+            CU(cudaMemcpyAsync(pin_gh + (size_t)i0 * 4, ls + l_gh, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, ls + l_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int l = 0; l < lanes; ++l) {
+        cudaError_t e_ = cudaStreamSynchronize(h->lane_streams[l]);
+        if (e_ != cudaSuccess && rc == BGP_OK) rc = fail(h, BGP_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e_));
+    }
+    if (rc == BGP_OK) {
+        memcpy(elbo, pin_elbo, (size_t)count * 8);
+        memcpy(status, pin_st, (size_t)count * 4);
+        if (want_grad) memcpy(grad_hyp, pin_gh, (size_t)count * 32);
+    }
     return rc;
 }
 
