@@ -16,13 +16,24 @@ constexpr int TILE_ELEMS = TS * TS;    // 1024 doubles
 constexpr int TILE_BYTES = TILE_ELEMS * 8;
 constexpr int TPM = 4;                 // tiles per macro-block side
 constexpr int MB = TS * TPM;           // macro block side (128)
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;          // assignment passes, vector kernels, sparse path
+#ifndef BGP_GEMM_WARPS
+#define BGP_GEMM_WARPS 16
+#endif
+// Tile GEMM kernels: 4 warps along the 128 rows x (GEMM_WARPS/4) warps along the 128 columns.  16 warps (32x32 warp
+// tiles, 4 warps per SM sub-partition) keep the DMMA pipe fed while one warp waits on LDS / mbarrier / instruction fetch.
+constexpr int GEMM_WARPS = BGP_GEMM_WARPS;
+constexpr int GEMM_THREADS = 32 * GEMM_WARPS;
+constexpr int WCOLS = GEMM_WARPS / 4;          // warps along the columns (2 or 4)
+constexpr int WN = MB / WCOLS;                 // columns per warp tile (64 or 32)
+constexpr int NI = WN / 8;                     // 8-column MMA tiles per warp (8 or 4)
+constexpr int NBT = WN / TS;                   // B tiles per warp (2 or 1)
 constexpr int NSTAGES = 3;
 constexpr int STAGE_ELEMS = 8 * TILE_ELEMS;          // 4 A tiles + 4 B tiles
 constexpr int STAGE_BYTES = STAGE_ELEMS * 8;          // 64 KB
 constexpr int PIPE_BYTES = NSTAGES * STAGE_BYTES;     // 192 KB
 constexpr int DLD = MB + 1;                           // padded leading dimension of the 128x128 smem scratch
-constexpr int SMEM_RED_DOUBLES = 3 * NTHREADS;
+constexpr int SMEM_RED_DOUBLES = 3 * 512;
 constexpr int SMEM_BYTES = PIPE_BYTES + SMEM_RED_DOUBLES * 8 + 64;   // + reduction scratch + 2*NSTAGES mbarriers
 
 constexpr double JITTER = 1e-6;        // gpflow.default_jitter()

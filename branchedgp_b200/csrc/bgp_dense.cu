@@ -118,9 +118,9 @@ __device__ void chol128(double* Dm, int& fail, int base_index) {
         const double r = sqrt(d);
         __syncthreads();
         if (tid == 0) Dm[j * DLD + j] = r;
-        for (int i = j + 1 + tid; i < MB; i += NTHREADS) Dm[i * DLD + j] /= r;
+        for (int i = j + 1 + tid; i < MB; i += GEMM_THREADS) Dm[i * DLD + j] /= r;
         __syncthreads();
-        for (int i = j + 1 + (tid >> 4); i < MB; i += 16) {
+        for (int i = j + 1 + (tid >> 4); i < MB; i += GEMM_THREADS / 16) {
             const double lij = Dm[i * DLD + j];
             for (int k = j + 1 + (tid & 15); k <= i; k += 16) Dm[i * DLD + k] -= lij * Dm[k * DLD + j];
         }
@@ -154,7 +154,7 @@ __device__ void store_lower_block(const double* Dm, int J, double* packed, doubl
             double* tp = packed ? packed + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS : nullptr;
             double* tb = block ? block + (size_t)(a * TPM + b) * TILE_ELEMS : nullptr;
             double* td = (dalt && a == b) ? dalt + (size_t)(TPM * J + a) * TILE_ELEMS : nullptr;
-            for (int e = tid; e < TILE_ELEMS; e += NTHREADS) {
+            for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
                 const int i = e >> 5, j = e & 31;
                 double v = Dm[(TS * a + i) * DLD + TS * b + j];
                 if (a == b && j > i) v = 0.0;
@@ -169,7 +169,7 @@ __device__ void store_lower_block(const double* Dm, int J, double* packed, doubl
 // ------------------------------------------------------------------------------------------------ k_chol
 // SRC == 0: factor K (generated on the fly) into LC, also LCe and LinvD.   SRC == 1: factor P (stored in RX) in place, RinvD, log-det.
 template <int SRC>
-__global__ void __launch_bounds__(NTHREADS, 1) k_chol(DenseParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_chol(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_syrk:  P = L^T Delta L + I  (L = Lc + eps I)
-__global__ void __launch_bounds__(NTHREADS, 1) k_syrk(DenseParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_trtri:  RX <- inv(R), in place
-__global__ void __launch_bounds__(NTHREADS, 1) k_trtri(DenseParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri(DenseParams P) {
             for (int b = 0; b <= a; ++b) {
                 const double* src = blk + (size_t)(a * TPM + b) * TILE_ELEMS;
                 double* dstp = RX + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS;
-                for (int e = tid; e < TILE_ELEMS; e += NTHREADS) dstp[e] = src[e];
+                for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) dstp[e] = src[e];
             }
         fence_proxy_async();
         __syncthreads();
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_lauum:  PB = -D/2 X^T X - 1/2 q q^T
-__global__ void __launch_bounds__(NTHREADS, 1) k_lauum(DenseParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_lauum(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_trmm:  G = L Pbar (lower), Lbar, delta partials
-__global__ void __launch_bounds__(NTHREADS, 1) k_trmm(DenseParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -485,10 +485,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trmm(DenseParams P) {
                 double r = rs[mi];
                 r += __shfl_xor_sync(0xffffffffu, r, 1);
                 r += __shfl_xor_sync(0xffffffffu, r, 2);
-                if (c == 0) red[(warp >> 2) * MB + (warp & 3) * TS + 8 * mi + g] = r;
+                if (c == 0) red[(warp >> 2) * MB + (warp & 3) * TS + 8 * mi + g] = r;   // one partial per column group of warps
             }
             __syncthreads();
-            if (tid < MB) dpart[(size_t)J * Mp + MB * I + tid] = red[tid] + red[MB + tid];
+            if (tid < MB) {
+                double r = 0.0;
+#pragma unroll
+                for (int w = 0; w < WCOLS; ++w) r += red[w * MB + tid];
+                dpart[(size_t)J * Mp + MB * I + tid] = r;
+            }
         }
 }
 
@@ -562,7 +567,7 @@ __device__ __forceinline__ void hyper_accum(const DenseParams& P, const double* 
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_adj(DenseParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -655,7 +660,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_adj(DenseParams P) {
                 const double* sab = S1 + (size_t)(a * TPM + b) * TILE_ELEMS;
                 const double* sba = S1 + (size_t)(b * TPM + a) * TILE_ELEMS;
                 double* tp = LB + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS;
-                for (int e = tid; e < TILE_ELEMS; e += NTHREADS) {
+                for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
                     const int i = e >> 5, j = e & 31;
                     const double w = sab[tswz(i, j)] + sba[tswz(j, i)];
                     tp[tswz(i, j)] = w;
@@ -694,7 +699,7 @@ __device__ __forceinline__ double kpair(const DenseParams& P, double t1, int f1,
     return (kbase(t1 - b, ell, kvar, P.kind) * kinv) * kbase(t2 - b, ell, kvar, P.kind);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_predict(DenseParams P, PredictArgs Q) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, PredictArgs Q) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
@@ -741,7 +746,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict(DenseParams P, PredictA
                 for (int a = 0; a < TPM; ++a)
                     for (int bb = 0; bb <= a; ++bb) {
                         const double* src = (a == bb) ? LCe + (size_t)(TPM * I + a) * TILE_ELEMS : LC + packed_tile(TPM * I + a, TPM * I + bb) * TILE_ELEMS;
-                        for (int e = tid; e < TILE_ELEMS; e += NTHREADS) {
+                        for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
                             const int i = e >> 5, j = e & 31;
                             Dm[(TS * a + i) * DLD + TS * bb + j] = src[tswz(i, j)];
                         }
@@ -768,12 +773,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict(DenseParams P, PredictA
     // mean and marginal variance: column reductions over the Mp rows
     double* red = smem_red(smem);
     {
-        const int s = tid & 127, half = tid >> 7;
+        const int s = tid & 127, half = tid >> 7;   // `half` = which of the GEMM_THREADS/128 row subsets this thread sums
         const double* cv = vec + VL.c;
         double sq = 0.0;
         for (int d0 = 0; d0 < D; d0 += 1) {
             double m = 0.0;
-            for (int i = half; i < Mp; i += 2) {
+            for (int i = half; i < Mp; i += GEMM_THREADS / 128) {
                 const double x2 = T2[(size_t)((i >> 5) * TPM + (s >> 5)) * TILE_ELEMS + tswz(i & 31, s & 31)];
                 m += x2 * cv[(size_t)d0 * Mp + i];
                 if (d0 == 0) {
@@ -784,12 +789,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict(DenseParams P, PredictA
             __syncthreads();
             red[tid] = m;
             __syncthreads();
-            if (tid < 128 && s < T) Q.mean[((size_t)slot * Q.Ttot + Q.s0 + s) * D + d0] = red[tid] + red[tid + 128];
+            if (tid < 128 && s < T) {
+                double r = 0.0;
+                for (int w = 0; w < GEMM_THREADS / 128; ++w) r += red[tid + 128 * w];
+                Q.mean[((size_t)slot * Q.Ttot + Q.s0 + s) * D + d0] = r;
+            }
         }
         __syncthreads();
         red[tid] = sq;
         __syncthreads();
-        if (!Q.full_cov && tid < 128 && s < T) Q.var[(size_t)slot * Q.Ttot + Q.s0 + s] = kvar + P.square_noise + red[tid] + red[tid + 128];
+        if (!Q.full_cov && tid < 128 && s < T) {
+            double r = kvar + P.square_noise;
+            for (int w = 0; w < GEMM_THREADS / 128; ++w) r += red[tid + 128 * w];
+            Q.var[(size_t)slot * Q.Ttot + Q.s0 + s] = r;
+        }
     }
     if (Q.full_cov) {
         // cov = K(Xnew) + tmp2^T tmp2 - tmp1^T tmp1   (128 x 128 Gram matrices through the tile GEMM)
@@ -821,7 +834,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict(DenseParams P, PredictA
 void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, int T, int Ttot, int s0, int full_cov, double* mean,
                           double* var, cudaStream_t st) {
     PredictArgs Q{Xnew, T, Ttot, s0, full_cov, mean, var};
-    k_predict<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P, Q);
+    k_predict<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
 }
 
 // ------------------------------------------------------------------------------------------------ debug: unpack a tile matrix to row-major
@@ -863,15 +876,15 @@ void dense_launch_prep(const DenseParams& P, const double* Apart, const double* 
 // phase: 1 chol K, 2 P, 3 chol P, 4 solve, 5 trtri, 6 lauum, 7 trmm, 8 post, 9 adjoint
 void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_t st) {
     switch (phase) {
-        case 1: k_chol<0><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
-        case 2: k_syrk<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
-        case 3: k_chol<1><<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 1: k_chol<0><<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
+        case 2: k_syrk<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
+        case 3: k_chol<1><<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         case 4: k_solve<<<nitems, NTHREADS, 0, st>>>(P); break;
-        case 5: k_trtri<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
-        case 6: k_lauum<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
-        case 7: k_trmm<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 5: k_trtri<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
+        case 6: k_lauum<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
+        case 7: k_trmm<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         case 8: k_post<<<nitems, NTHREADS, 0, st>>>(P); break;
-        case 9: k_adj<<<nitems, NTHREADS, SMEM_BYTES, st>>>(P); break;
+        case 9: k_adj<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         default: break;
     }
 }

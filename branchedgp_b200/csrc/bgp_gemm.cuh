@@ -69,20 +69,20 @@ __device__ __forceinline__ void pipe_init(Pipe& p, unsigned char* smem) {
     p.empty = p.full + NSTAGES;
     p.it = 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGES; ++s) { mbar_init(p.full + s, 1); mbar_init(p.empty + s, NTHREADS / 32); }
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(p.full + s, 1); mbar_init(p.empty + s, GEMM_WARPS); }
         fence_mbar_init();
     }
     __syncthreads();
 }
 __device__ __forceinline__ double* smem_red(unsigned char* smem) { return reinterpret_cast<double*>(smem + PIPE_BYTES); }
 
-typedef double Acc[4][8][2];
+typedef double Acc[4][NI][2];
 
 __device__ __forceinline__ void acc_zero(Acc& acc) {
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 }
 
 // One 32-wide k-step of the warp tile.  FULL: both 32-column halves of the warp's 64 columns are live (no predication);
@@ -102,10 +102,10 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
     int toff[4];
 #pragma unroll
     for (int o8 = 0; o8 < 4; ++o8) toff[o8] = tbase + ((8 * o8 + g) ^ c2);
-    const bool h0 = FULL || (nmask & 1), h1 = FULL || (nmask & 2);
+    const bool h0 = FULL || (nmask & 1), h1 = (NBT == 2) && (FULL || (nmask & 2));
 #pragma unroll KUNROLL
     for (int k4 = 0; k4 < 8; ++k4) {
-        double af[4], bf[8];
+        double af[4], bf[NI];
         const int kx = ((4 * k4) ^ g3);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) af[mi] = As[TA ? (toff[mi] + 4 * k4 * TS) : (nbase + 8 * mi * TS + kx)];
@@ -115,7 +115,7 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
             for (int mi = 0; mi < 4; ++mi) af[mi] *= s;
         }
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
+        for (int ni = 0; ni < NI; ++ni) {
             const int o8 = ni & 3;
             const double* Bt = (ni >> 2) ? Bs1 : Bs0;
             const int off = TB ? (toff[o8] + 4 * k4 * TS) : (nbase + 8 * o8 * TS + kx);
@@ -128,11 +128,11 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
-        if (h1) {
+        if (NBT == 2 && h1) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 4; ni < 8; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                for (int ni = 4; ni < NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
     }
 }
@@ -145,14 +145,14 @@ __device__ __forceinline__ void warp_kstep_dispatch(Acc& acc, bool ta, bool tb, 
 }
 
 // acc += Aop[ao0*32 .. +128][kt0*32 .. kt1*32) * Bop[bo0*32 .. +128][same k]^T, optionally with the k index scaled
-// by kscale[k].  Must be called by all NTHREADS threads with identical arguments.
+// by kscale[k].  Must be called by all GEMM_THREADS threads with identical arguments.
 __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, int ao0, const Opnd& B, int bo0, int kt0,
                                            int kt1, const double* __restrict__ kscale) {
     const int nk = kt1 - kt0;
     if (nk <= 0) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
-    const int wa = warp & 3, wb = (warp >> 2) * 2;
+    const int wa = warp & 3, wb = (warp >> 2) * NBT;
 
     auto issue = [&](int ks) {
         const uint32_t it = pipe.it + (uint32_t)ks;
@@ -197,7 +197,9 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
         bool ta, tb0, tb1;
         const double* pa = resolve(A, ao0 + wa, kt, ta);
         const double* pb0 = resolve(B, bo0 + wb, kt, tb0);
-        const double* pb1 = resolve(B, bo0 + wb + 1, kt, tb1);
+        const double* pb1 = nullptr;
+        tb1 = tb0;
+        if (NBT == 2) pb1 = resolve(B, bo0 + wb + 1, kt, tb1);
         if (pa == nullptr) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
         int nmask = (pb0 != nullptr ? 1 : 0) | (pb1 != nullptr ? 2 : 0);
         if (nmask == 0) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
@@ -206,7 +208,7 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
         const double* Bs0 = sb + (size_t)(4 + wb) * TILE_ELEMS;
         const double* Bs1 = Bs0 + TILE_ELEMS;
         const double* ksc = kscale ? kscale + (size_t)kt * TS : nullptr;
-        if (nmask == 3 && tb0 == tb1) {
+        if (nmask == (NBT == 2 ? 3 : 1) && tb0 == tb1) {
             warp_kstep_dispatch<true>(acc, ta, tb0, As, Bs0, Bs1, 3, ksc, g, c);
         } else {
             if (nmask & 1) warp_kstep_dispatch<false>(acc, ta, tb0, As, Bs0, Bs1, 1, ksc, g, c);
@@ -224,11 +226,11 @@ template <class F>
 __device__ __forceinline__ void acc_foreach(Acc& acc, int I, int J, F f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, c = lane & 3;
-    const int wa = warp & 3, wb = (warp >> 2) * 2;
+    const int wa = warp & 3, wb = (warp >> 2) * NBT;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni)
+        for (int ni = 0; ni < NI; ++ni)
             f(TPM * I + wa, TPM * J + wb + (ni >> 2), 8 * mi + g, 8 * (ni & 3) + 2 * c, acc[mi][ni][0], acc[mi][ni][1]);
 }
 
