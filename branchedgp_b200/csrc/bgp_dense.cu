@@ -274,9 +274,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_solve: z, c, q
-__global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
+constexpr int SOLVE_THREADS = 1024;   // memory-bound vector kernel: many warps = many tile loads in flight
+constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
+constexpr int SOLVE_NH = SOLVE_WARPS / 4;   // warps sharing one 32-row (or 32-column) strip of a macro block
+
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(DenseParams P) {
     DENSE_SETUP();
-    __shared__ double part[NTHREADS];
+    __shared__ double part[SOLVE_THREADS];
     __shared__ double yv[MB];
     __shared__ double red[32];
     const int warp = tid >> 5, lane = tid & 31;
@@ -287,13 +291,14 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
         double* z = vec + VL.z + (size_t)d * Mp;
         double* cv = vec + VL.c + (size_t)d * Mp;
         double* q = vec + VL.q + (size_t)d * Mp;
-        // z = (Lc + eps I)^T v : z[j] = sum_{i >= j} L[i][j] v[i]
-        for (int jt = warp; jt < nT; jt += NTHREADS / 32) {
+        // z = (Lc + eps I)^T v : z[j] = sum_{i >= j} L[i][j] v[i]; long and short tile columns are interleaved over the warps
+        for (int idx = warp; idx < nT; idx += SOLVE_WARPS) {
+            const int jt = (idx & 1) ? (nT - 1 - (idx >> 1)) : (idx >> 1);
             double s = 0.0;
             for (int it = jt; it < nT; ++it) {
                 const double* tile = (it == jt) ? LCe + (size_t)it * TILE_ELEMS : LC + packed_tile(it, jt) * TILE_ELEMS;
                 const double* vv = v + it * TS;
-#pragma unroll 8
+#pragma unroll
                 for (int i = 0; i < TS; ++i) s += tile[tswz(i, lane)] * vv[i];
             }
             z[jt * TS + lane] = s;
@@ -305,17 +310,22 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
                 const int a = warp & 3, h = warp >> 2;
                 const int it = TPM * J + a;
                 double s = 0.0;
-                for (int kt = h; kt < TPM * J; kt += 2) {
+                for (int kt = h; kt < TPM * J; kt += SOLVE_NH) {
                     const double* row = RX + packed_tile(it, kt) * TILE_ELEMS + lane * TS;
                     const double* cc = cv + kt * TS;
                     const int sw = (lane & 3) << 2;
-#pragma unroll 8
+#pragma unroll
                     for (int k = 0; k < TS; ++k) s += row[k ^ sw] * cc[k];
                 }
                 part[tid] = s;
             }
             __syncthreads();
-            if (tid < MB) yv[tid] = z[MB * J + tid] - part[tid] - part[tid + MB];
+            if (tid < MB) {
+                double s = z[MB * J + tid];
+#pragma unroll
+                for (int h = 0; h < SOLVE_NH; ++h) s -= part[tid + MB * h];
+                yv[tid] = s;
+            }
             __syncthreads();
             if (tid < MB) {
                 const double* blk = RinvD + (size_t)J * 16 * TILE_ELEMS;
@@ -324,6 +334,7 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
                 for (int b = 0; b <= a; ++b) {
                     const double* row = blk + (size_t)(a * TPM + b) * TILE_ELEMS + i * TS;
                     const int sw = (i & 3) << 2;
+#pragma unroll
                     for (int k = 0; k < TS; ++k) s += row[k ^ sw] * yv[b * TS + k];
                 }
                 cv[MB * J + tid] = s;
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
             __syncthreads();
         }
         // c = cu / s
-        for (int j = tid; j < Mp; j += NTHREADS) {
+        for (int j = tid; j < Mp; j += SOLVE_THREADS) {
             const double x = cv[j] / likvar;
             cv[j] = x;
             sumc2 += x * x;
@@ -343,16 +354,21 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
                 const int b = warp & 3, h = warp >> 2;
                 const int jt = TPM * J + b;
                 double s = 0.0;
-                for (int it = TPM * (J + 1) + h; it < nT; it += 2) {
+                for (int it = TPM * (J + 1) + h; it < nT; it += SOLVE_NH) {
                     const double* tile = RX + packed_tile(it, jt) * TILE_ELEMS;
                     const double* qq = q + it * TS;
-#pragma unroll 8
+#pragma unroll
                     for (int i = 0; i < TS; ++i) s += tile[tswz(i, lane)] * qq[i];
                 }
                 part[tid] = s;
             }
             __syncthreads();
-            if (tid < MB) yv[tid] = cv[MB * J + tid] - part[tid] - part[tid + MB];
+            if (tid < MB) {
+                double s = cv[MB * J + tid];
+#pragma unroll
+                for (int h = 0; h < SOLVE_NH; ++h) s -= part[tid + MB * h];
+                yv[tid] = s;
+            }
             __syncthreads();
             if (tid < MB) {
                 const double* blk = RinvD + (size_t)J * 16 * TILE_ELEMS;
@@ -360,6 +376,7 @@ __global__ void __launch_bounds__(NTHREADS) k_solve(DenseParams P) {
                 double s = 0.0;
                 for (int a = b; a < TPM; ++a) {
                     const double* tile = blk + (size_t)(a * TPM + b) * TILE_ELEMS;
+#pragma unroll
                     for (int k = 0; k < TS; ++k) s += tile[tswz(k, j)] * yv[a * TS + k];
                 }
                 q[MB * J + tid] = s;
@@ -498,13 +515,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_post: delta, Abar, vbar, d/d likvar, ELBO
-__global__ void __launch_bounds__(NTHREADS) k_post(DenseParams P) {
+__global__ void __launch_bounds__(SOLVE_THREADS) k_post(DenseParams P) {
     DENSE_SETUP();
     __shared__ double red[32];
     const int warp = tid >> 5, lane = tid & 31;
     const int Mp = dm.Mp, M = dm.M, nT = dm.nT, D = dm.D, N = dm.N;
     double adel = 0.0;
-    for (int i = tid; i < Mp; i += NTHREADS) {
+    for (int i = tid; i < Mp; i += SOLVE_THREADS) {
         const int I = i / MB;
         double s = 0.0;
         for (int J = 0; J <= I; ++J) s += vec[VL.dpart + (size_t)J * Mp + i];
@@ -517,13 +534,14 @@ __global__ void __launch_bounds__(NTHREADS) k_post(DenseParams P) {
     for (int d = 0; d < D; ++d) {
         const double* q = vec + VL.q + (size_t)d * Mp;
         double* vb = vec + VL.vbar + (size_t)d * Mp;
-        for (int it = warp; it < nT; it += NTHREADS / 32) {
+        for (int idx = warp; idx < nT; idx += SOLVE_WARPS) {
+            const int it = (idx & 1) ? (nT - 1 - (idx >> 1)) : (idx >> 1);   // interleave long and short tile rows
             double s = 0.0;
             const int sw = (lane & 3) << 2;
             for (int jt = 0; jt <= it; ++jt) {
                 const double* row = ((it == jt) ? LCe + (size_t)it * TILE_ELEMS : LC + packed_tile(it, jt) * TILE_ELEMS) + lane * TS;
                 const double* qq = q + jt * TS;
-#pragma unroll 8
+#pragma unroll
                 for (int k = 0; k < TS; ++k) s += row[k ^ sw] * qq[k];
             }
             vb[it * TS + lane] = s / likvar;
@@ -879,11 +897,11 @@ void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_
         case 1: k_chol<0><<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         case 2: k_syrk<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         case 3: k_chol<1><<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
-        case 4: k_solve<<<nitems, NTHREADS, 0, st>>>(P); break;
+        case 4: k_solve<<<nitems, SOLVE_THREADS, 0, st>>>(P); break;
         case 5: k_trtri<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         case 6: k_lauum<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         case 7: k_trmm<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
-        case 8: k_post<<<nitems, NTHREADS, 0, st>>>(P); break;
+        case 8: k_post<<<nitems, SOLVE_THREADS, 0, st>>>(P); break;
         case 9: k_adj<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         default: break;
     }

@@ -16,7 +16,11 @@
 
 namespace bgp {
 
-constexpr int KUNROLL = BGP_KUNROLL;   // unroll factor of the k4 loop of warp_kstep
+constexpr int KUNROLL = BGP_KUNROLL;
+#ifndef BGP_PRODUCER_LAST
+#define BGP_PRODUCER_LAST 1
+#endif
+constexpr int PRODUCER_TID = BGP_PRODUCER_LAST ? (GEMM_THREADS - 32) : 0;   // unroll factor of the k4 loop of warp_kstep
 
 enum { ACC_ROWK = 0, ACC_COLK = 1, ACC_SYM = 2 };
 enum { LAY_PACKED = 0, LAY_BLOCK = 1 };
@@ -173,8 +177,11 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
             if (src[i] != nullptr) tma_load_1d(sb + (size_t)i * TILE_ELEMS, src[i], TILE_BYTES, bar);
     };
 
+    // The producer is lane 0 of the LAST warp: the warp arbiter favours high warp ids, so that warp reaches each k-step
+    // first and the refill is requested as early as the ring allows (with warp 0 as producer the loads were issued by the
+    // slowest warp and every other warp then waited for the data: ncu long_scoreboard 17 % on the full-barrier spin).
     __syncthreads();   // every warp is done with the ring (previous GEMM or scratch use)
-    if (tid == 0) {
+    if (tid == PRODUCER_TID) {
         const int pre = nk < (NSTAGES - 1) ? nk : (NSTAGES - 1);
         for (int p = 0; p < pre; ++p) {
             const uint32_t itn = pipe.it + (uint32_t)p;
@@ -184,7 +191,7 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
     }
     for (int ks = 0; ks < nk; ++ks) {
         if (ks + NSTAGES - 1 < nk) {
-            if (tid == 0) {   // refill the slot released NSTAGES-1 k-steps ago once all 8 warps have arrived on its `empty` barrier
+            if (tid == PRODUCER_TID) {   // refill the slot released NSTAGES-1 k-steps ago once all 8 warps have arrived on its `empty` barrier
                 const uint32_t itn = pipe.it + (uint32_t)(ks + NSTAGES - 1);
                 if (itn >= NSTAGES) mbar_wait(pipe.empty + itn % NSTAGES, ((itn / NSTAGES) - 1u) & 1u);
                 issue(ks + NSTAGES - 1);
