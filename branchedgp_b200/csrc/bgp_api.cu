@@ -89,7 +89,7 @@ static DenseDims make_dims(int N, int D) {
 }
 
 struct SlotLayout {   // byte offsets inside one slot
-    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, vec, Apart, vpart, klpart, lse, total;
+    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, total;
 };
 static SlotLayout slot_layout(const DenseDims& d) {
     SlotLayout L;
@@ -100,6 +100,7 @@ static SlotLayout slot_layout(const DenseDims& d) {
     L.LinvD = take((size_t)d.nM * 16 * TILE_ELEMS);
     L.RinvD = take((size_t)d.nM * 16 * TILE_ELEMS);
     L.SCR = take((size_t)2 * 16 * TILE_ELEMS);
+    L.KT = take((size_t)2 * d.N * d.N);
     L.vec = take(d.vec_elems);
     L.Apart = take((size_t)d.nch * d.Mp);
     L.vpart = take((size_t)d.nch * d.D * d.Mp);
@@ -195,7 +196,7 @@ static int dense_run(bgp_handle* h, int count, int N, int D, const double* t, co
     P.t = t; P.hyp = hyp; P.bv = b; P.KConst = KConst;
     P.LC = (double*)(base + SL.LC); P.RX = (double*)(base + SL.RX); P.PB = (double*)(base + SL.PB); P.LB = (double*)(base + SL.LB);
     P.LCe = (double*)(base + SL.LCe); P.LinvD = (double*)(base + SL.LinvD); P.RinvD = (double*)(base + SL.RinvD);
-    P.SCR = (double*)(base + SL.SCR); P.vec = (double*)(base + SL.vec);
+    P.SCR = (double*)(base + SL.SCR); P.KT = (double*)(base + SL.KT); P.vec = (double*)(base + SL.vec);
     P.status = status; P.elbo = elbo; P.grad_hyp = grad_hyp;
     P.slot_stride = (long long)stride_d;
 
@@ -220,7 +221,8 @@ static int dense_run(bgp_handle* h, int count, int N, int D, const double* t, co
         pm(-1);
         phi_launch_forward(F, n, st);
         pm(0);
-        dense_launch_prep(P, F.Apart, F.vpart, F.klpart, Y, item_gene, n, st);
+        dense_launch_prep(P, F.Apart, F.vpart, F.klpart, Y, item_gene, n, st);   // k_prep (+ k_ktable unless KConst)
+        if (KConst == nullptr) h->launches++;
         pm(1);
         for (int phase = 1; phase <= 9 && phase <= last; ++phase) {
             const bool grad_phase = (phase == 5 || phase == 6 || phase == 7 || phase == 9);

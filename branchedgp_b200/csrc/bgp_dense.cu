@@ -89,16 +89,33 @@ __global__ void __launch_bounds__(NTHREADS) k_prep(DenseParams P, PrepArgs Q) {
     }
 }
 
+// Base-kernel table: every same-function entry K[(i,f),(j,f)] = k(t_i - t_j) is needed 3 times by the covariance epilogue
+// and 3 times by the hyper-gradient; one exp per cell pair here replaces one per matrix entry there.
+__global__ void __launch_bounds__(NTHREADS) k_ktable(DenseParams P) {
+    const int slot = blockIdx.y, item = P.item0 + slot;
+    const int N = P.d.N;
+    const double ell = P.hyp[(size_t)item * 3 + 0], kvar = P.hyp[(size_t)item * 3 + 1];
+    double* KT = P.KT + (size_t)slot * P.slot_stride;
+    const long long nn = (long long)N * N;
+    for (long long e = (long long)blockIdx.x * NTHREADS + threadIdx.x; e < nn; e += (long long)gridDim.x * NTHREADS) {
+        const int i = (int)(e / N), j = (int)(e % N);
+        double k, dl, dd;
+        kbase_grads(P.t[i] - P.t[j], ell, kvar, P.kind, k, dl, dd);
+        KT[e] = k;
+        KT[nn + e] = dl;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ covariance
 // K[(t,f),(t',f')] for cell-major rows 3*cell + f  (VBHelperFunctions.py:170-194; branch_kernParamGPflow.py:117-198).
-__device__ __forceinline__ double kgen(const DenseParams& P, const double* __restrict__ ka, int gi, int gj, double ell,
-                                       double kvar, double kinv) {
+__device__ __forceinline__ double kgen(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ KT, int gi,
+                                       int gj, double kinv) {
     const int M = P.d.M;
     if (gi >= M || gj >= M) return gi == gj ? 1.0 : 0.0;   // identity padding
     if (P.KConst != nullptr) return P.KConst[(size_t)gi * M + gj];
     const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
     double k;
-    if (fi == fj) k = kbase(P.t[ci] - P.t[cj], ell, kvar, P.kind);
+    if (fi == fj) k = KT[(size_t)ci * P.d.N + cj];
     else k = (ka[ci] * kinv) * ka[cj];
     if (gi == gj) k += P.square_noise;
     return k;
@@ -178,6 +195,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
     double* dst = SRC == 0 ? LC : RX;
     double* invD = SRC == 0 ? LinvD : RinvD;
     const double* ka = vec + VL.ka;
+    const double* KT = P.KT + (size_t)slot * P.slot_stride;
     const double kinv = 1.0 / (kvar + JITTER);   // inv(k(b,b) + jitter), branch_kernParamGPflow.py:168-189
     const int nM = dm.nM;
     int fail = 0;
@@ -194,8 +212,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
             const int gi = it * TS + i, gj = jt * TS + j;
             double s0, s1;
             if (SRC == 0) {
-                s0 = kgen(P, ka, gi, gj, ell, kvar, kinv);
-                s1 = kgen(P, ka, gi, gj + 1, ell, kvar, kinv);
+                s0 = kgen(P, ka, KT, gi, gj, kinv);
+                s1 = kgen(P, ka, KT, gi, gj + 1, kinv);
             } else {
                 const double2 p = tile_load2(dst + packed_tile(it, jt) * TILE_ELEMS, i, j);
                 s0 = p.x; s1 = p.y;
@@ -227,8 +245,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
                 double s0, s1;
                 if (SRC == 0) {
                     const int gi = it * TS + i, gj = jt * TS + j;
-                    s0 = kgen(P, ka, gi, gj, ell, kvar, kinv);
-                    s1 = kgen(P, ka, gi, gj + 1, ell, kvar, kinv);
+                    s0 = kgen(P, ka, KT, gi, gj, kinv);
+                    s1 = kgen(P, ka, KT, gi, gj + 1, kinv);
                 } else {
                     const double2 p = tile_load2(tp, i, j);
                     s0 = p.x; s1 = p.y;
@@ -565,17 +583,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_post(DenseParams P) {
 // ------------------------------------------------------------------------------------------------ k_adj
 // sum over the stored lower triangle of Ktilde o dK/dtheta.  w carries 2*Kbar_ij off the diagonal and Kbar_ii on it.
 __device__ __forceinline__ void hyper_accum(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ dkal,
-                                            const double* __restrict__ dkab, int gi, int gj, double w, double ell, double kvar,
-                                            double kinv, double& gl, double& gv, double& gb) {
+                                            const double* __restrict__ dkab, const double* __restrict__ KT, int gi, int gj, double w,
+                                            double kvar, double kinv, double& gl, double& gv, double& gb) {
     const int M = P.d.M;
     if (gi >= M || gj >= M || gj > gi) return;
     if (gi == gj) w *= 0.5;
     const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
     if (fi == fj) {
-        double k, dl, dd;
-        kbase_grads(P.t[ci] - P.t[cj], ell, kvar, P.kind, k, dl, dd);
-        gl += w * dl;
-        gv += w * k / kvar;
+        const size_t e = (size_t)ci * P.d.N + cj;
+        gl += w * KT[(size_t)P.d.N * P.d.N + e];
+        gv += w * KT[e] / kvar;
     } else {
         const double a = ka[ci], b = ka[cj];
         const double cr = (a * kinv) * b;
@@ -594,6 +611,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
     const double* ka = vec + VL.ka;
     const double* dkal = vec + VL.dkal;
     const double* dkab = vec + VL.dkab;
+    const double* KT = P.KT + (size_t)slot * P.slot_stride;
     const double kinv = 1.0 / (kvar + JITTER);
     const bool want_hyp = (P.KConst == nullptr);
     double gl = 0.0, gv = 0.0, gb = 0.0;
@@ -624,8 +642,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
                 tile_store2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
                 if (want_hyp) {
                     const int gi = it * TS + i, gj = jt * TS + j;
-                    hyper_accum(P, ka, dkal, dkab, gi, gj, v0, ell, kvar, kinv, gl, gv, gb);
-                    hyper_accum(P, ka, dkal, dkab, gi, gj + 1, v1, ell, kvar, kinv, gl, gv, gb);
+                    hyper_accum(P, ka, dkal, dkab, KT, gi, gj, v0, kvar, kinv, gl, gv, gb);
+                    hyper_accum(P, ka, dkal, dkab, KT, gi, gj + 1, v1, kvar, kinv, gl, gv, gb);
                 }
             });
             fence_proxy_async();
@@ -682,7 +700,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
                     const int i = e >> 5, j = e & 31;
                     const double w = sab[tswz(i, j)] + sba[tswz(j, i)];
                     tp[tswz(i, j)] = w;
-                    if (want_hyp) hyper_accum(P, ka, dkal, dkab, (TPM * J + a) * TS + i, (TPM * J + b) * TS + j, w, ell, kvar, kinv, gl, gv, gb);
+                    if (want_hyp) hyper_accum(P, ka, dkal, dkab, KT, (TPM * J + a) * TS + i, (TPM * J + b) * TS + j, w, kvar, kinv, gl, gv, gb);
                 }
             }
         fence_proxy_async();
@@ -889,6 +907,10 @@ void dense_launch_prep(const DenseParams& P, const double* Apart, const double* 
                        const int* item_gene, int nitems, cudaStream_t st) {
     PrepArgs Q{Apart, vpart, klpart, Y, item_gene};
     k_prep<<<nitems, NTHREADS, 0, st>>>(P, Q);
+    if (P.KConst == nullptr) {
+        const int gx = (int)(((long long)P.d.N * P.d.N + NTHREADS * 8 - 1) / (NTHREADS * 8));
+        k_ktable<<<dim3(gx < 1 ? 1 : gx, nitems), NTHREADS, 0, st>>>(P);
+    }
 }
 
 // phase: 1 chol K, 2 P, 3 chol P, 4 solve, 5 trtri, 6 lauum, 7 trmm, 8 post, 9 adjoint

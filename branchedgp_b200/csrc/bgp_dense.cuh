@@ -59,6 +59,7 @@ struct DenseParams {
     double* LCe;              // nT diagonal tiles of chol(K) + jitter*I
     double* LinvD; double* RinvD;                     // nM blocks of 16 tiles (inverse diagonal macro blocks)
     double* SCR;              // 2 blocks of 16 tiles
+    double* KT;               // [2][N][N] base-kernel table k(t_i - t_j) and its lengthscale derivative (same-function entries of K)
     double* vec;              // vector area, see vec_layout()
     int* status;              // [count]
     // outputs (device)
