@@ -79,6 +79,7 @@ static DenseDims make_dims(int N, int D) {
     d.Mp = (d.M + MB - 1) / MB * MB;
     d.nT = d.Mp / TS;
     d.nM = d.Mp / MB;
+    d.nTv = (d.M + TS - 1) / TS;
     d.D = D;
     d.nch = (N + PHI_RCH - 1) / PHI_RCH;
     // PB / LB double as tall nT x 4 tile matrices in k_predict, which is larger than the packed triangle when nT < 7

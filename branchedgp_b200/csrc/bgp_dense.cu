@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk(DenseParams P) {
     for (int I = 0; I < dm.nM; ++I)
         for (int J = 0; J <= I; ++J) {
             acc_zero(acc);
-            gemm_macro(acc, pipe, opL, TPM * I, opL, TPM * J, TPM * I, dm.nT, Delta);
+            gemm_macro(acc, pipe, opL, TPM * I, opL, TPM * J, TPM * I, dm.nTv, Delta);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 if (it < jt) return;
                 const int gi = it * TS + i, gj = jt * TS + j;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri(DenseParams P) {
         for (int I = nM - 1; I > J; --I) {
             // acc = sum_{J<k<=I} X[I,k] R[k,J]
             acc_zero(acc);
-            gemm_macro(acc, pipe, opRow, TPM * I, opCol, TPM * J, TPM * (J + 1), TPM * I + TPM, nullptr);
+            gemm_macro(acc, pipe, opRow, TPM * I, opCol, TPM * J, TPM * (J + 1), min(TPM * I + TPM, dm.nTv), nullptr);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 tile_store2(RX + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
             });
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_lauum(DenseParams P) {
     for (int I = 0; I < dm.nM; ++I)
         for (int J = 0; J <= I; ++J) {
             acc_zero(acc);
-            gemm_macro(acc, pipe, opX, TPM * I, opX, TPM * J, TPM * I, dm.nT, nullptr);
+            gemm_macro(acc, pipe, opX, TPM * I, opX, TPM * J, TPM * I, dm.nTv, nullptr);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 if (it < jt) return;
                 const int gi = it * TS + i, gj = jt * TS + j;
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
     for (int I = 0; I < dm.nM; ++I)
         for (int J = 0; J <= I; ++J) {
             acc_zero(acc);
-            gemm_macro(acc, pipe, opL, TPM * I, opP, TPM * J, 0, TPM * I + TPM, nullptr);
+            gemm_macro(acc, pipe, opL, TPM * I, opP, TPM * J, 0, min(TPM * I + TPM, dm.nTv), nullptr);
             double rs[4] = {0.0, 0.0, 0.0, 0.0};
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 if (it < jt) return;
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
     Pipe pipe;
     pipe_init(pipe, smem);
     double* red = smem_red(smem);
-    const int nM = dm.nM, nT = dm.nT;
+    const int nM = dm.nM, nT = dm.nTv;   // k-ranges stop at the last tile that holds a row < M
     const double* ka = vec + VL.ka;
     const double* dkal = vec + VL.dkal;
     const double* dkab = vec + VL.dkab;

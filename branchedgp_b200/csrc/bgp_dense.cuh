@@ -12,6 +12,7 @@ enum { SC_LOGDET = 0, SC_SUMC2 = 1, SC_KL = 2, SC_SUMY2 = 3, SC_ADELTA = 4, SC_T
 
 struct DenseDims {
     int N, M, Mp, nT, nM, D, nch;   // cells, 3N, padded, tiles per side, macro blocks per side, outputs, row chunks of the Phi pass
+    int nTv;                        // tiles that contain a row < M: k-ranges stop here (identity padding contributes nothing to valid entries)
     long long mat_elems;            // doubles in one packed block-lower matrix
     long long vec_elems;            // doubles in one per-item vector area
 };
