@@ -222,8 +222,16 @@ def run_ours(args):
     pk = fp64_peak()
     gemm_ms = sum(phase_ms[k] for k in fl)
     total_flops = sum(fl.values()) * ips * args.steps
+    traffic = None   # dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (148-item launch)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
+            cap = json.load(f).get({"adjoint": "k_adj", "lauum": "k_lauum"}.get(dom, dom), {})
+        if "dram_bytes_read" in cap and abs(items_per_launch - 148.0) < 1e-9 and N == 1000:
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 3), "peak": pk["dmma_tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["dmma_tflops"], 4), "traffic": None,
+                "frac": round(achieved / pk["dmma_tflops"], 4), "traffic": traffic,
                 "launch_ms": round(launch_ms, 3), "items_per_launch": items_per_launch,
                 "flops_per_item": fl[dom], "peak_source": pk["source"], "cublas_dgemm_tflops": pk["cublas_dgemm_tflops"],
                 "whole_step_tflops": round(total_flops / (ms * 1e-3) / 1e12, 3),
