@@ -471,14 +471,18 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
         const int n = (count - item0 < items_cap) ? (count - item0) : items_cap;
         const int nslots = n * SD;
         P.item0 = item0; F.item0 = item0;
+        // profiling slots reuse the dense phase ids: 0 phi forward, 1 prep, 2 Kuu, 3 forward slabs, 4 mid, 5 backward slabs,
+        // 6 end + reduce, 11 phi backward
+        prof_mark(h, -1, st);
         phi_launch_forward(F, nslots, st);
-        h->launches++;
+        prof_mark(h, 0, st);
         for (int phase = 0; phase <= 5; ++phase) {
             if (phase == 4 && !want_grad) continue;
             sparse_launch_phase(P, nslots, phase, sub_out, st);
-            h->launches += (phase == 5) ? 2 : 1;
+            if (phase == 5 || phase == 0) h->launches++;
+            prof_mark(h, phase + 1, st);
         }
-        if (want_grad) { phi_launch_backward(F, n, st); h->launches++; }
+        if (want_grad) { phi_launch_backward(F, n, st); prof_mark(h, 11, st); }
         CU(cudaGetLastError());
     }
     h->lastS = P;

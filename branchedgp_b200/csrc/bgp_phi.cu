@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     const int nr = min(PHI_RCH, N - r0);
     const double* lp = P.logPhi + ((size_t)item * N + r0) * M;
     const double b = P.bv[(size_t)P.item0 * P.SD + slot];
-    // ---- row log-sum-exp, one warp per row
+    // ---- row log-sum-exp, one warp per row (max pass, then exp-sum pass; a branchy one-pass online variant measured slower)
     for (int rr = warp; rr < nr; rr += NTHREADS / 32) {
         const double* row = lp + (size_t)rr * M;
         double m = -1.0e308;

@@ -68,26 +68,38 @@ __device__ void trinv_packed(double* A, int n) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- k_sp_reduce_partials
+// A_j, Delta_j, v_jd from the row-chunk partials of the assignment pass; grid (column blocks, slots) so that the
+// nch x Mp partial arrays (300 MB per item at N = 10 000) are read with the whole GPU, in a fixed order (deterministic).
+__global__ void __launch_bounds__(NTHREADS) k_sp_reduce_partials(SparseParams P) {
+    const int slot = blockIdx.y;
+    const int item = P.item0 + slot / P.SD;
+    const int Mp = P.Mp, M = P.M, D = P.D, nch = P.nch;
+    const SparseLayout SLy = sparse_layout(P.N, Mp, P.Mz, D, P.nsplit, nch);
+    double* const ws = P.ws + (size_t)slot * P.slot_stride;
+    const double likvar = P.hyp[(size_t)item * 3 + 2];
+    const int j = blockIdx.x * NTHREADS + threadIdx.x;
+    if (j >= Mp) return;
+    double a = 0.0;
+    if (j < M)
+        for (int ch = 0; ch < nch; ++ch) a += ws[SLy.Apart + (size_t)ch * Mp + j];
+    ws[SLy.A + j] = a;
+    ws[SLy.Delta + j] = a / likvar;
+    for (int d = 0; d < D; ++d) {
+        double s = 0.0;
+        if (j < M)
+            for (int ch = 0; ch < nch; ++ch) s += ws[SLy.vpart + ((size_t)ch * D + d) * Mp + j];
+        ws[SLy.v + (size_t)d * Mp + j] = s;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- k_sp_prep
 __global__ void __launch_bounds__(NTHREADS) k_sp_prep(SparseParams P) {
     SP_SETUP();
     __shared__ double red[32];
     const int nch = P.nch;
     double suma = 0.0;
-    for (int j = tid; j < Mp; j += NTHREADS) {
-        double a = 0.0;
-        if (j < M)
-            for (int ch = 0; ch < nch; ++ch) a += ws[SLy.Apart + (size_t)ch * Mp + j];
-        ws[SLy.A + j] = a;
-        ws[SLy.Delta + j] = a / likvar;
-        suma += a;
-        for (int d = 0; d < D; ++d) {
-            double s = 0.0;
-            if (j < M)
-                for (int ch = 0; ch < nch; ++ch) s += ws[SLy.vpart + ((size_t)ch * D + d) * Mp + j];
-            ws[SLy.v + (size_t)d * Mp + j] = s;
-        }
-    }
+    for (int j = tid; j < Mp; j += NTHREADS) suma += ws[SLy.A + j];   // A, Delta, v were reduced by k_sp_reduce_partials
     for (int i = tid; i < N; i += NTHREADS) {
         double k, dl, dd;
         kbase_grads(P.t[i] - bpt, ell, kvar, P.kind, k, dl, dd);
@@ -590,7 +602,10 @@ cudaError_t sparse_init_kernels() {
 void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* sub_out, cudaStream_t st) {
     dim3 g1(1, nslots), gs(P.nsplit, nslots);
     switch (phase) {
-        case 0: k_sp_prep<<<g1, NTHREADS, 0, st>>>(P); break;
+        case 0:
+            k_sp_reduce_partials<<<dim3((P.Mp + NTHREADS - 1) / NTHREADS, nslots), NTHREADS, 0, st>>>(P);
+            k_sp_prep<<<g1, NTHREADS, 0, st>>>(P);
+            break;
         case 1: k_sp_kuu<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
         case 2: k_sp_fwd<<<gs, NTHREADS, slab_bytes(P.Mz, 2), st>>>(P); break;
         case 3: k_sp_mid<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;

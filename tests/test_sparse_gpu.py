@@ -69,3 +69,41 @@ def test_mbgp_multi_output_sparse_matches_oracle(engine, N, D, nz):
     assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
     assert relerr(out["grad_b"][0], g["Bv"]) <= GRAD_RTOL
     assert np.allclose(out["grad_hyp"][0], [g["ell"], g["var"], g["likvar"]], rtol=GRAD_RTOL, atol=1e-6 * np.abs(out["grad_hyp"][0]).max())
+
+
+def test_c4_shape_mbgp_n500_d100_mz180(engine):
+    """BASELINE configs[3] shape: MBGP joint assignment, N = 500 cells, D = 100 outputs, 60 inducing times x 3 functions."""
+    N, D = 500, 100
+    pr = make_problem(N, D=D, seed=77, mbgp=True)
+    t = pr["t"]
+    _, trunk = host_ref.init_logphi_mbgp(pr["phi0"], t)
+    eZ0 = host_ref.expand_prior_mbgp(pr["prior3"])
+    Zt = np.linspace(0, 1, 60, endpoint=False)
+    Z = np.array([[z, f] for z in Zt for f in (1, 2, 3)], dtype=float)
+    Bv = np.random.default_rng(1).uniform(0.1, 0.9, D)
+    h = np.array([[0.5, 1.0, 0.05]])
+    e, g = bgp_numpy.mbgp_sparse_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], Z, t, eZ0, trunk, Bv, h[0, 0], h[0, 1], h[0, 2])
+    out = engine.sparse_elbo_grad(t, Z, pr["Y"], pr["item_gene"][:1], Bv[None], pr["prior3"], h, pr["logPhi"][:1],
+                                  kernel=_lib.KERNEL_SQEXP, model=_lib.MODEL_MBGP, multi=True)
+    assert out["status"][0] == 0
+    assert abs(out["elbo"][0] - e) <= ELBO_RTOL * abs(e), (out["elbo"][0], e)
+    assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
+    assert relerr(out["grad_b"][0], g["Bv"]) <= GRAD_RTOL
+    assert np.allclose(out["grad_hyp"][0], [g["ell"], g["var"], g["likvar"]], rtol=GRAD_RTOL, atol=1e-6 * np.abs(out["grad_hyp"][0]).max())
+
+
+def test_c3_shape_sparse_bgp_large_n(engine):
+    """BASELINE configs[2] shape scaled to what the oracle finishes in seconds: N = 3000 cells, 30 inducing points
+    (the full N = 10 000 case differs only in the number of rows / slabs streamed)."""
+    N = 3000
+    pr = make_problem(N, D=1, n_genes=1, bs=(0.45,), seed=78)
+    Z = _Z(30)
+    b, h = pr["b"][0], pr["hyp"][0]
+    e, g = bgp_numpy.sparse_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], Z, _pz(pr, b), b, h[0], h[1], h[2])
+    out = engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"])
+    assert out["status"][0] == 0
+    assert abs(out["elbo"][0] - e) <= ELBO_RTOL * abs(e), (out["elbo"][0], e)
+    assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
+    scale = max(abs(g["ell"]), abs(g["var"]), abs(g["likvar"]))
+    for j, nm in enumerate(("ell", "var", "likvar")):
+        assert abs(out["grad_hyp"][0, j] - g[nm]) <= GRAD_RTOL * max(abs(g[nm]), 1e-3 * scale), (nm, out["grad_hyp"][0, j], g[nm])

@@ -1,0 +1,81 @@
+"""Throughput of the inducing-point paths at the BASELINE shapes C3 (sparse BGP) and C4 (MBGP) with device-resident inputs."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from branchedgp_b200 import _lib  # noqa: E402
+
+
+def run(name, N, Dtot, Mz, count, multi, reps=3):
+    dev = torch.device("cuda:0")
+    eng = _lib.Engine(0)
+    lib, h = eng._lib, eng._h
+    g = torch.Generator().manual_seed(0)
+    M = 3 * N
+    t = torch.sort(torch.rand(N, generator=g, dtype=torch.float64)).values.to(dev)
+    nz = Mz // 3 if multi else Mz
+    if multi:
+        zt = torch.linspace(0, 1, nz + 1, dtype=torch.float64)[:-1]
+        Z = torch.stack([zt.repeat_interleave(3), torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64).repeat(nz)], 1).to(dev)
+    else:
+        zt = torch.linspace(0, 1, Mz + 1, dtype=torch.float64)[:-1]
+        Z = torch.stack([zt, torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64).repeat(Mz)[:Mz]], 1).to(dev)
+    Y = torch.randn(1, N, Dtot, generator=g, dtype=torch.float64).to(dev)
+    SD = Dtot if multi else 1
+    b = (0.1 + 0.8 * torch.rand(count, SD, generator=g, dtype=torch.float64)).to(dev)
+    prior = torch.full((N, 3 if multi else 2), 0.5, dtype=torch.float64, device=dev)
+    if multi:
+        prior[:, 0] = 0.0
+    hyp = torch.tensor([[0.5, 1.0, 0.05]], dtype=torch.float64).repeat(count, 1).to(dev)
+    gene = torch.zeros(count, dtype=torch.int32, device=dev)
+    logPhi = torch.full((count, N, M), -9.0, dtype=torch.float64, device=dev)
+    logPhi += 0.1 * torch.randn(count, N, M, dtype=torch.float64, device=dev)
+    ar = torch.arange(N, device=dev)
+    for f in range(3):
+        logPhi[:, ar, 3 * ar + f] = float(np.log(1 / 3))
+    elbo = torch.empty(count, dtype=torch.float64, device=dev)
+    gh = torch.zeros(count, 3, dtype=torch.float64, device=dev)
+    gb = torch.zeros(count, SD, dtype=torch.float64, device=dev)
+    gl = torch.empty_like(logPhi)
+    st = torch.zeros(count, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        rc = lib.bgp_sparse_elbo_grad(h, count, N, Dtot, Mz, t.data_ptr(), Z.data_ptr(), Y.data_ptr(), 1, gene.data_ptr(), b.data_ptr(),
+                                      prior.data_ptr(), hyp.data_ptr(), 1 if multi else 0, 1 if multi else 0, 1 if multi else 0,
+                                      logPhi.data_ptr(), 1, elbo.data_ptr(), gh.data_ptr(), gb.data_ptr(), gl.data_ptr(), st.data_ptr(),
+                                      stream)
+        assert rc == 0, lib.bgp_last_error(h)
+
+    call()
+    torch.cuda.synchronize()
+    eng.profile_enable(True)
+    eng.profile_reset()
+    call()
+    ph, _ = eng.profile_read()
+    eng.profile_enable(False)
+    names = dict(phi_forward="phi_fwd", prep="prep", chol_K="kuu", syrk_P="fwd_slabs", chol_P="mid", solve="bwd_slabs", trtri="end",
+                 phi_backward="phi_bwd")
+    print(json.dumps({names[k]: round(v, 3) for k, v in ph.items() if k in names}))
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    bytes_alg = 2.0 * 8 * N * M * count
+    print(json.dumps({"config": name, "N": N, "D": Dtot, "Mz": Mz, "items": count, "ms": round(best, 3),
+                      "items_per_s": round(count / best * 1e3, 2), "logPhi_GBps": round(bytes_alg / best / 1e6, 1),
+                      "status_nonzero": int((st != 0).sum().item()), "elbo0": float(elbo[0].item())}))
+
+
+if __name__ == "__main__":
+    run("C3 sparse BGP", 10000, 1, 30, int(sys.argv[1]) if len(sys.argv) > 1 else 8, False)
+    run("C4 MBGP", 500, 100, 180, 4, True)
