@@ -138,3 +138,38 @@ def test_mbgp_fitmodel_learns_branching_points(num_inputs):
     assert fit["prediction"]["mu"][0].shape == (100, num_inputs)
     for true_bp, inferred_bp in zip(true_bps, fit["Bmode"][:num_inputs]):
         assert abs(true_bp - inferred_bp) < 0.01, f"True branching points: {true_bps}. Inferred: {fit['Bmode']}"
+
+
+@pytest.mark.parametrize("which", ["scipy", "amazing", "randomising"])
+def test_mbgp_training_helpers_optimisers(which):
+    """testing/MBGP/test_synthetic_data.py::test_demo__using_other_training_methods (two genes)."""
+    from branchedgp_b200.MBGP.data_generation import ToyBranchedData
+    from branchedgp_b200.MBGP.training_helpers import (ElvijsAmazingOptimiser, ElvijsRandomisingOptimiser, ScipyOptimiser,
+                                                       SimplePhiConstructor, construct_and_fit_assigngp_model, get_training_outcome)
+    np.random.seed(0)
+    true_bps = [0.2, 0.4]
+    data = ToyBranchedData(B=true_bps, N=30)
+    opt = {"scipy": ScipyOptimiser(), "amazing": ElvijsAmazingOptimiser(),
+           "randomising": ElvijsRandomisingOptimiser(base_optimiser=ScipyOptimiser(), num_samples=300)}[which]
+    model = construct_and_fit_assigngp_model(data, phi_constructor=SimplePhiConstructor(data, prior_confidence=0.65),
+                                             initial_branching_points=[0.01, 0.15], optimiser=opt)
+    outcome = get_training_outcome(model)
+    assert outcome.predictions.y_mean[0].shape == (100, 2)
+    assert np.all(np.isfinite(outcome.predictions.y_var[1]))
+    if which != "scipy":   # plain L-BFGS from early branching points is not expected to find them (the reference only tests the others)
+        assert np.all(np.abs(np.array(true_bps) - outcome.learned_branching_points) < 0.01), outcome.learned_branching_points
+
+
+def test_batched_branching_point_scan_matches_sequential():
+    from branchedgp_b200.MBGP.data_generation import ToyBranchedData
+    from branchedgp_b200.MBGP.training_helpers import SimplePhiConstructor, construct_assigngp_model
+    np.random.seed(1)
+    data = ToyBranchedData(B=[0.3, 0.6], N=20)
+    m = construct_assigngp_model(data, SimplePhiConstructor(data, prior_confidence=0.65), [0.2, 0.2])
+    cand = np.random.uniform(size=(5, 2))
+    batched = m.training_losses_for_branching_points(cand)
+    seq = []
+    for c in cand:
+        m.kernel.Bv.assign(c)
+        seq.append(m.training_loss())
+    assert np.allclose(batched, seq, rtol=1e-6, atol=0)   # Bv round-trips through the sigmoid transform in the sequential path
