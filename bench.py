@@ -284,7 +284,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (logPhi+grad = %.1f GB per step), no flush" % (2 * ips * N * 3 * N * 8 / 1e9),
                        "parallelism": f"items sharded over {world} GPU(s), NCCL all_gather of [items,5] results per step"},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "status_nonzero": bad}
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(N, H, kind="port", budget_s=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -305,10 +305,27 @@ def _host_problem(N, H, k):
     return lp, H["Y"][gene[0]], X, pZ, b, H["hyp"][idx[0]]
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms are meant to use every host core."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(N, H, kind, budget_s=20.0, impl="numpy"):
     """Time the CPU oracle (test infrastructure; the one sanctioned use outside tests) on a bounded sample of the workload."""
     import torch
     from oracle import bgp_numpy, bgp_torch
+    _use_all_host_threads()
     fn = bgp_numpy.dense_value_and_grad if impl == "numpy" else bgp_torch.dense_value_and_grad
     times, k = [], 0
     t_start = time.perf_counter()
@@ -338,6 +355,7 @@ def run_reference(args):
     N = args.cells
     H = synth_host(N)
     from oracle import bgp_torch
+    _use_all_host_threads()
     k = 0
     times = []
     per_step = max(1, args.ref_items)
