@@ -157,13 +157,78 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_backward(PhiParams P) {
 }
 
 // nsubs = sub-problems (slots) in the wave;  nitems = nsubs / SD
+// Row-resident variant of the backward pass: one CTA per row of logPhi, the row's S and Sbar live in registers
+// (EPT elements per thread), so logPhi is read once and the gradient written once, with one exp and one log per element
+// (the warp-per-row kernel above re-reads the row and recomputes the exp for its second pass).  grid (N, items).
+template <int BT, int EPT>
+__global__ void __launch_bounds__(BT) k_phi_backward_rows(PhiParams P) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x, litem = blockIdx.y, item = P.item0 + litem;
+    const int N = P.N, M = P.M, Mp = P.Mp, D = P.D, SD = P.SD;
+    const double log_eps = log(1e-6);
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* bvi = P.bv + (size_t)item * SD;
+    const size_t slot0 = (size_t)litem * SD;
+    const double* x = P.logPhi + ((size_t)item * N + row) * M;
+    double* gout = P.grad_logPhi + ((size_t)item * N + row) * M;
+    const double ti = P.t[row];
+    int nact = 0;
+    for (int sd = 0; sd < SD; ++sd) nact += (P.model == MODEL_BGP || ti > bvi[sd]) ? 1 : 0;
+    if (nact == 0) {   // uniform over the CTA
+        for (int j = tid; j < M; j += BT) gout[j] = 0.0;
+        return;
+    }
+    const bool act0 = ti > bvi[0];
+    const double l = P.lse[slot0 * P.slot_stride + row];
+    double S[EPT], sb[EPT];
+    double r = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int j = tid + e * BT;
+        S[e] = 0.0; sb[e] = 0.0;
+        if (j < M) {
+            const int cell = j / 3, f = j - 3 * cell;
+            const bool inblock = (cell == row);
+            const double s_ = exp(x[j] - l);
+            const double phi = SQ_A * s_ + SQ_B;
+            double acc = 0.0;
+            for (int sd = 0; sd < SD; ++sd) {
+                if (!(P.model == MODEL_BGP || ti > bvi[sd])) continue;
+                const double* Abar = P.Abar + (slot0 + sd) * P.slot_stride;
+                const double* vbar = P.vbar + (slot0 + sd) * P.slot_stride;
+                const int yc = (SD > 1) ? sd : 0;
+                double yv = 0.0;
+                for (int d = 0; d < D; ++d) yv += Yg[(size_t)row * P.Dtot + yc + d] * vbar[(size_t)d * Mp + j];
+                acc += Abar[j] + yv;
+            }
+            const double lpz = log_pz(P.model, P.model == MODEL_BGP ? act0 : true, inblock, f, P.prior, row, log_eps);
+            const double v = SQ_A * (acc - P.kl_weight * (double)nact * (log(phi) + 1.0 - lpz));
+            S[e] = s_; sb[e] = v;
+            r += s_ * v;
+        }
+    }
+    r = block_sum(r, red);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int j = tid + e * BT;
+        if (j < M) gout[j] = S[e] * (sb[e] - r);
+    }
+}
+
 void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
     dim3 grid(P.nch, nsubs);
     k_phi_forward<<<grid, NTHREADS, 0, st>>>(P);
 }
 void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
-    dim3 grid(P.nch, nitems);
-    k_phi_backward<<<grid, NTHREADS, 0, st>>>(P);
+    dim3 rows(P.N, nitems);
+    if (P.M <= 256 * 4) k_phi_backward_rows<256, 4><<<rows, 256, 0, st>>>(P);
+    else if (P.M <= 256 * 12) k_phi_backward_rows<256, 12><<<rows, 256, 0, st>>>(P);
+    else if (P.M <= 512 * 12) k_phi_backward_rows<512, 12><<<rows, 512, 0, st>>>(P);
+    else {   // rows too long for one CTA's registers: warp-per-row two-pass kernel
+        dim3 grid(P.nch, nitems);
+        k_phi_backward<<<grid, NTHREADS, 0, st>>>(P);
+    }
 }
 
 }  // namespace bgp
