@@ -87,6 +87,108 @@ def FitModel(bConsider, GPt, GPy, globalBranching, priorConfidence=0.80, M=10, l
             "hyperparameters": hyps[iw], "posteriorB": postB}
 
 
+def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=10, likvar=1.0, kerlen=2.0, kervar=5.0,
+                  fDebug=False, maxiter=100, fPredict=True, fixHyperparameters=False, engine=None, max_slots=0):
+    """``FitModel`` for every gene (column of ``GPY`` [N, G]) at once: returns a list of G dictionaries with FitModel's keys.
+
+    Per gene the semantics are FitModel's (FitBranchingModel.py:11-178): the same initial conditions and label prior for
+    every gene, ``logPhi`` re-initialised at every candidate branching point, trainable hyper-parameters warm-started from
+    one grid point to the next, log posterior density as ``loglik``, and the error branch (NaN in ``loglik[0]``) when a
+    factorisation fails.  What changes is where the optimiser runs: all genes are fitted together by the device-resident
+    batched L-BFGS of ``libbgp_b200`` (bgp_dense_fit_host for M = 0, bgp_sparse_fit_host otherwise) -- one call per grid
+    point with G work items when the hyper-parameters are trainable (the warm start makes the grid a serial chain per
+    gene), one call with G x len(bConsider) items when ``fixHyperparameters``."""
+    from . import _lib
+    assert isinstance(bConsider, list), "Candidate B must be list"
+    GPt = np.asarray(GPt, dtype=np.float64)
+    GPY = np.asarray(GPY, dtype=np.float64)
+    assert GPt.ndim == 1
+    assert GPY.ndim == 2 and GPY.shape[0] == GPt.size, "expression must be [cells, genes]"
+    assert globalBranching.size == GPt.size, "state space must be same size as number of cells"
+    assert M >= 0, "at least 0 or more inducing points should be given"
+    N, G = GPY.shape
+    B = len(bConsider)
+    eng = engine if engine is not None else _lib.default_engine()
+    phiInitial, phiPrior = GetInitialConditionsAndPrior(globalBranching, priorConfidence, infPriorPhi=True)
+    VBHelperFunctions.GetFunctionIndexListGeneral(GPt)   # consumes numpy's global RNG exactly like FitModel
+    Z = None
+    if M > 0:
+        Z = np.ones((M, 2))
+        Z[:, 0] = np.linspace(0, 1, M, endpoint=False)
+        Z[:, 1] = np.array([i for j in range(M) for i in range(1, 4)])[:M]
+    opts = eng.fit_options(maxiter=int(maxiter), train_hyp=0 if fixHyperparameters else 1, max_slots=int(max_slots))
+    Y = np.ascontiguousarray(GPY.T[:, :, None])          # [G, N, 1]
+    lo, hi = float(np.min(GPt)), float(np.max(GPt))
+
+    def test_inputs(b):
+        cols = [np.linspace(lo, b, 100), np.linspace(b, hi, 100), np.linspace(b, hi, 100)]
+        return np.vstack([np.stack([c, np.full(100, float(f))], axis=1) for f, c in zip((1, 2, 3), cols)])
+
+    ll = np.zeros((G, B))
+    hyp_at = np.empty((G, B, 3))
+    phi_at = np.empty((G, B, N, 3))
+    pred_mu = np.empty((G, B, 300, 1)) if fPredict else None
+    pred_var = np.empty((G, B, 300)) if fPredict else None
+    failed = np.zeros(G, dtype=bool)
+    fit_info = [dict(iters=np.zeros(B, dtype=int), nfev=np.zeros(B, dtype=int), status=np.zeros(B, dtype=int)) for _ in range(G)]
+
+    def run(genes, ibs, hyp0):
+        bs = np.array([bConsider[ib] for ib in ibs], dtype=np.float64)
+        Xnew = np.stack([test_inputs(b) for b in bs]) if fPredict else None
+        out = eng.fit(GPt, Y, genes, bs, phiPrior, phiInitial, hyp0, Z=Z, options=opts, Xnew=Xnew)
+        for k, (g, ib) in enumerate(zip(genes, ibs)):
+            ll[g, ib] = out["objective"][k]
+            hyp_at[g, ib] = out["hyp"][k]
+            phi_at[g, ib] = out["phi"][k]
+            if fPredict:
+                pred_mu[g, ib] = out["pred_mean"][k]
+                pred_var[g, ib] = out["pred_var"][k]
+            for key in ("iters", "nfev", "status"):
+                fit_info[g][key][ib] = out[key][k]
+            if out["status"][k] == 5 and not failed[g]:
+                failed[g] = True
+                print(f"Unexpected error: Cholesky decomposition was not successful (gene {g}, b={bConsider[ib]})")
+        return out
+
+    if fixHyperparameters:
+        genes = np.repeat(np.arange(G), B)
+        ibs = np.tile(np.arange(B), G)
+        run(genes, ibs, np.tile([kerlen, kervar, likvar], (G * B, 1)))
+    else:
+        cur = np.tile([kerlen, kervar, likvar], (G, 1)).astype(np.float64)
+        for ib in range(B):
+            genes = np.flatnonzero(~failed)
+            if genes.size == 0:
+                break
+            out = run(genes, [ib] * genes.size, cur[genes])
+            cur[genes] = out["hyp"]
+
+    results = []
+    for g in range(G):
+        if failed[g]:
+            bad = np.zeros(B)
+            bad[0] = np.nan
+            results.append({"loglik": bad, "model": None, "Phi": np.nan, "prediction": {"xtest": np.nan, "mu": np.nan, "var": np.nan},
+                            "hyperparameters": np.nan, "posteriorB": np.nan, "fit": fit_info[g]})
+            continue
+        iw = int(np.argmax(ll[g]))
+        postB = GetPosteriorB(ll[g], bConsider)
+        assert np.allclose(bConsider[iw], postB["Bmode"]), "%s-%s" % (str(postB["B_CI"]), bConsider[iw])
+        if fPredict:
+            X = test_inputs(bConsider[iw])
+            pred = {"xtest": [X[100 * f:100 * (f + 1), :1] for f in range(3)],
+                    "mu": [pred_mu[g, iw, 100 * f:100 * (f + 1)] for f in range(3)],
+                    "var": [pred_var[g, iw, 100 * f:100 * (f + 1), None] for f in range(3)]}
+        else:
+            pred = {"xtest": [], "mu": [], "var": []}
+        results.append({"loglik": ll[g].copy(), "Phi": phi_at[g, iw],
+                        "prediction": pred,
+                        "hyperparameters": {"likvar": np.array(hyp_at[g, iw, 2]), "kerlen": np.array(hyp_at[g, iw, 0]),
+                                            "kervar": np.array(hyp_at[g, iw, 1])},
+                        "posteriorB": postB, "fit": fit_info[g]})
+    return results
+
+
 def GetPosteriorB(objUnsorted, BgridSearch, ciLimits=[0.01, 0.99]):
     """Posterior over the grid of branching points, its mode and the indices of the confidence limits
     (FitBranchingModel.py:181-222)."""

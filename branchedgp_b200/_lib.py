@@ -61,6 +61,13 @@ SIGNATURES = {
                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
     "bgp_get_phi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_fit_default_options": (None, [ctypes.c_void_p]),
+    "bgp_dense_fit_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 2 + [ctypes.c_int]
+                           + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 11),
+    "bgp_sparse_fit_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+                            + [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 11),
+    "bgp_debug_linesearch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double]),
+    "bgp_debug_lbfgs_direction": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bgp_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "bgp_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
@@ -69,6 +76,17 @@ SIGNATURES = {
     "bgp_debug_dense_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "bgp_debug_dense_vector": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
+
+
+class FitOptions(ctypes.Structure):
+    """bgp_fit_options of include/branchedgp_b200.h (SciPy L-BFGS-B defaults, FitModel's hyper-priors)."""
+    _fields_ = [("maxiter", ctypes.c_int), ("maxcor", ctypes.c_int), ("maxls", ctypes.c_int), ("maxfun", ctypes.c_int),
+                ("ftol", ctypes.c_double), ("gtol", ctypes.c_double), ("train_hyp", ctypes.c_int), ("has_prior", ctypes.c_int * 3),
+                ("prior_mean", ctypes.c_double * 3), ("prior_sd", ctypes.c_double * 3), ("max_slots", ctypes.c_int)]
+
+
+FIT_STATUS = ("converged: max |g| <= gtol", "converged: relative reduction of f <= ftol", "stopped: maxiter", "stopped: maxfun",
+              "abnormal termination in line search", "Cholesky decomposition was not successful")
 
 
 class BgpError(RuntimeError):
@@ -269,6 +287,68 @@ class Engine:
                                                int(kernel), _ptr(logPhi), T, _ptr(Xnew), int(bool(full_cov)), _ptr(mean), _ptr(var))
         self._check(rc, "bgp_sparse_predict_host")
         return mean, var
+
+    # ------------------------------------------------------------------ batched fitting (device-resident L-BFGS)
+    def fit_options(self, **kw):
+        """bgp_fit_default_options with keyword overrides (maxiter, maxcor, maxls, maxfun, ftol, gtol, train_hyp, has_prior,
+        prior_mean, prior_sd, max_slots)."""
+        o = FitOptions()
+        self._lib.bgp_fit_default_options(ctypes.byref(o))
+        for k, v in kw.items():
+            if k in ("has_prior", "prior_mean", "prior_sd"):
+                arr = getattr(o, k)
+                for i in range(3):
+                    arr[i] = v[i]
+            else:
+                if not hasattr(o, k):
+                    raise TypeError(f"unknown fit option {k!r}")
+                setattr(o, k, v)
+        return o
+
+    def fit(self, t, Y, item_gene, b, prior, phiInitial, hyp0, Z=None, kernel=KERNEL_MATERN32, options=None, Xnew=None,
+            return_logPhi=False):
+        """Fit `count` work items (gene item_gene[i], branching point b[i], initial hyper-parameters hyp0[i]) at once.
+
+        Dense AssignGP when Z is None, AssignGPSparse with inducing inputs Z [Mz,2] otherwise.  Xnew [count,T,2]: test inputs
+        of predict_f per item.  Returns dict(objective, elbo, hyp, phi, pred_mean, pred_var, iters, nfev, status[, logPhi])."""
+        t = _f64(t)
+        Y = _f64(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        nY, N, D = Y.shape
+        item_gene = np.ascontiguousarray(item_gene, dtype=np.int32)
+        count = item_gene.size
+        b = _f64(b).reshape(count)
+        hyp0 = _f64(hyp0).reshape(count, 3)
+        prior = _f64(prior)
+        phiInitial = _f64(phiInitial)
+        assert t.shape == (N,) and prior.shape == (N, 2) and phiInitial.shape == (N, 2)
+        assert count > 0 and item_gene.min() >= 0 and item_gene.max() < nY
+        if options is None:
+            options = self.fit_options()
+        T = 0
+        if Xnew is not None:
+            Xnew = _f64(Xnew)
+            assert Xnew.ndim == 3 and Xnew.shape[0] == count and Xnew.shape[2] == 2
+            T = Xnew.shape[1]
+        out = dict(objective=np.empty(count), elbo=np.empty(count), hyp=np.empty((count, 3)), phi=np.empty((count, N, 3)),
+                   pred_mean=np.empty((count, T, D)) if T else None, pred_var=np.empty((count, T)) if T else None,
+                   iters=np.empty(count, dtype=np.int32), nfev=np.empty(count, dtype=np.int32), status=np.empty(count, dtype=np.int32))
+        lp = np.empty((count, N, 3 * N)) if return_logPhi else None
+        tail = [_ptr(b), _ptr(prior), _ptr(phiInitial), _ptr(hyp0), int(kernel), ctypes.addressof(options), T, _ptr(Xnew),
+                _ptr(out["objective"]), _ptr(out["elbo"]), _ptr(out["hyp"]), _ptr(out["phi"]), _ptr(out["pred_mean"]),
+                _ptr(out["pred_var"]), _ptr(out["iters"]), _ptr(out["nfev"]), _ptr(out["status"]), _ptr(lp)]
+        if Z is None:
+            rc = self._lib.bgp_dense_fit_host(self._h, count, N, D, _ptr(t), _ptr(Y), nY, _ptr(item_gene), *tail)
+            self._check(rc, "bgp_dense_fit_host")
+        else:
+            Z = _f64(Z)
+            assert Z.ndim == 2 and Z.shape[1] == 2
+            rc = self._lib.bgp_sparse_fit_host(self._h, count, N, D, Z.shape[0], _ptr(t), _ptr(Z), _ptr(Y), nY, _ptr(item_gene), *tail)
+            self._check(rc, "bgp_sparse_fit_host")
+        if return_logPhi:
+            out["logPhi"] = lp
+        return out
 
     def get_phi(self, logPhi):
         logPhi = _f64(logPhi)

@@ -1,48 +1,9 @@
 // extern "C" boundary of libbgp_b200.so (declared in include/branchedgp_b200.h): handle, workspace, wave loop.
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <vector>
-
-#include "../../include/branchedgp_b200.h"
-#include "bgp_launch.h"
+#include "bgp_internal.h"
 
 using namespace bgp;
 
-struct bgp_handle {
-    int device = 0;
-    int sm_count = 0;
-    int max_slots = 0;         // 0 = default
-    int stop_phase = 0;
-    char err[512] = {0};
-    // workspace (grow-only)
-    void* ws = nullptr;
-    size_t ws_bytes = 0;
-    // staging for the _host entry points (grow-only)
-    void* stage = nullptr;
-    size_t stage_bytes = 0;
-    // description of the last dense wave, for the debug readers
-    DenseParams lastP;
-    SparseParams lastS;        // parameters of the last sparse wave (device pointers into the staging area stay valid
-    bool keep_sparse = false;  //  until the next call), used by bgp_sparse_predict_host
-    int last_slots = 0;
-    bool kernels_ready = false;
-    std::vector<cudaStream_t> lane_streams;   // streams of the host-pointer entry points (one per in-flight item group)
-    cudaEvent_t shared_ready = nullptr;
-    void* pin = nullptr;       // pinned host scratch for the small per-item results of the host-pointer entry points
-    size_t pin_bytes = 0;
-    // optional per-kernel timing (bench.py): events recorded around every launch of a call
-    bool profiling = false;
-    std::vector<cudaEvent_t> ev_pool;
-    std::vector<std::pair<int, int>> ev_marks;   // (phase id, index into ev_pool of the event recorded AFTER the launch)
-    int ev_used = 0;
-    // set by bgp_dense_predict_host around a forward-only dense call
-    const double* pred_X = nullptr; int pred_T = 0; int pred_full = 0; double* pred_mean = nullptr; double* pred_var = nullptr;
-    double prof_ms[BGP_NPHASES] = {0};
-    long long launches = 0;
-};
-
-static void prof_mark(bgp_handle* h, int phase, cudaStream_t st) {
+void prof_mark(bgp_handle* h, int phase, cudaStream_t st) {
     if (phase >= 0) h->launches++;
     if (!h->profiling) return;
     if (h->ev_used == (int)h->ev_pool.size()) {
@@ -55,7 +16,7 @@ static void prof_mark(bgp_handle* h, int phase, cudaStream_t st) {
     h->ev_used++;
 }
 
-static int fail(bgp_handle* h, int code, const char* fmt, ...) {
+int fail(bgp_handle* h, int code, const char* fmt, ...) {
     if (h) {
         va_list ap;
         va_start(ap, fmt);
@@ -64,15 +25,7 @@ static int fail(bgp_handle* h, int code, const char* fmt, ...) {
     }
     return code;
 }
-#define CU(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) return fail(h, BGP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
-
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-static DenseDims make_dims(int N, int D) {
+DenseDims make_dims(int N, int D) {
     DenseDims d;
     d.N = N;
     d.M = 3 * N;
@@ -89,10 +42,7 @@ static DenseDims make_dims(int N, int D) {
     return d;
 }
 
-struct SlotLayout {   // byte offsets inside one slot
-    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, total;
-};
-static SlotLayout slot_layout(const DenseDims& d) {
+SlotLayout slot_layout(const DenseDims& d) {
     SlotLayout L;
     size_t o = 0;
     auto take = [&](size_t doubles) { size_t r = o; o = align_up(o + doubles * 8, 256); return r; };
@@ -156,7 +106,8 @@ size_t bgp_dense_slot_bytes(int N, int D) { return slot_layout(make_dims(N, D)).
 int bgp_host_alloc(void** p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BGP_OK : BGP_ERR_NOMEM; }
 int bgp_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BGP_OK : BGP_ERR_CUDA; }
 
-static int ensure_ws(bgp_handle* h, size_t bytes) {
+}  // extern "C"
+int ensure_ws(bgp_handle* h, size_t bytes) {
     if (h->ws_bytes >= bytes) return BGP_OK;
     if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
     cudaError_t e = cudaMalloc(&h->ws, bytes);
@@ -164,6 +115,7 @@ static int ensure_ws(bgp_handle* h, size_t bytes) {
     h->ws_bytes = bytes;
     return BGP_OK;
 }
+extern "C" {
 
 static int pick_slots(bgp_handle* h, int count, size_t slot_bytes) {
     int cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
@@ -177,9 +129,10 @@ static int pick_slots(bgp_handle* h, int count, size_t slot_bytes) {
     return cap;
 }
 
+}  // extern "C"
 // One call's worth of waves on `st`, using `slots` workspace slots starting at `base`.  `global_item0` is the index of the
 // call's first item in caller-global arrays that are not staged per call (the predict outputs).
-static int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, const int* item_gene, const double* b,
+int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, const int* item_gene, const double* b,
                      const double* prior, const double* hyp, int kernel_kind, int model, double kl_weight, const double* logPhi,
                      const double* KConst, int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status,
                      char* base, int slots, cudaStream_t st, bool mark, int global_item0) {
@@ -251,6 +204,7 @@ static int dense_run(bgp_handle* h, int count, int N, int D, const double* t, co
     h->lastP = P;
     return BGP_OK;
 }
+extern "C" {
 
 static int dense_check_args(bgp_handle* h, int count, int N, int D, int nY, const void* t, const void* Y, const void* item_gene,
                             const void* b, const void* prior, const void* hyp, int kernel_kind, int model, const void* logPhi,
@@ -282,7 +236,8 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
 }
 
 // ---- host-pointer variant ---------------------------------------------------------------------------------------
-static int ensure_stage(bgp_handle* h, size_t bytes) {
+}  // extern "C"
+int ensure_stage(bgp_handle* h, size_t bytes) {
     if (h->stage_bytes >= bytes) return BGP_OK;
     if (h->stage) { cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
     cudaError_t e = cudaMalloc(&h->stage, bytes);
@@ -290,6 +245,7 @@ static int ensure_stage(bgp_handle* h, size_t bytes) {
     h->stage_bytes = bytes;
     return BGP_OK;
 }
+extern "C" {
 
 // Host-pointer entry.  The items are cut into groups of about a quarter of the SMs; each group owns a lane (CUDA stream +
 // workspace slots + staging buffers) on which its H2D copy, kernels and D2H copy are queued in order.  Up to four groups

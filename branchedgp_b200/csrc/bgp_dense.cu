@@ -22,7 +22,7 @@ namespace bgp {
 #define DENSE_SETUP()                                                                              \
     extern __shared__ __align__(128) unsigned char smem[];                                         \
     const int tid = threadIdx.x;                                                                   \
-    const int slot = blockIdx.x;                                                                   \
+    const int slot = P.slot_map ? P.slot_map[blockIdx.x] : (int)blockIdx.x;                        \
     const int item = P.item0 + slot;                                                               \
     const DenseDims& dm = P.d;                                                                     \
     const VecLayout VL = vec_layout(dm.Mp, dm.nM, dm.D);                                           \
@@ -725,6 +725,9 @@ struct PredictArgs {
     int T;                // inputs in this launch, <= 128
     int Ttot, s0;         // total number of test inputs of the call and offset of this launch (output row indexing)
     int full_cov;         // only with Ttot <= 128
+    int rx_inverse;       // RX already holds R^-1 (state after the gradient phases): tmp2 = R^-1 tmp1 is a product, not a solve
+    long long xnew_stride;// doubles between the test inputs of consecutive slots (0: all slots share Xnew)
+    int par_chunks;       // grid.y = chunks of 128 test inputs, each with its own scratch inside PB / LB (T, s0 derived per chunk)
     double* mean;         // [slot][T][D]
     double* var;          // [slot][T] or [slot][T][T]
 };
@@ -740,13 +743,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
     Pipe pipe;
     pipe_init(pipe, smem);
     double* Dm = pipe.stages;
-    const int nM = dm.nM, nT = dm.nT, M = dm.M, T = Q.T, D = dm.D, Mp = dm.Mp;
+    const int nM = dm.nM, nT = dm.nT, M = dm.M, D = dm.D, Mp = dm.Mp;
+    const int chunk = Q.par_chunks ? (int)blockIdx.y : 0;
+    const int qs0 = Q.par_chunks ? chunk * MB : Q.s0;
+    const int T = Q.par_chunks ? ((Q.Ttot - qs0 < MB) ? (Q.Ttot - qs0) : MB) : Q.T;
+    const double* Xn = Q.Xnew + (size_t)slot * Q.xnew_stride + (Q.par_chunks ? 2 * (size_t)qs0 : 0);
+    const size_t tall = (size_t)nT * TPM * TILE_ELEMS;   // one tall nT x 4 tile matrix
     const double b = P.bv[item];
     const double kinv = 1.0 / (kvar + JITTER);
-    double* S0 = SCR;
-    double* S1 = SCR + 16 * TILE_ELEMS;
-    double* T1 = PB;   // tall tile matrices: tile (r, c) at (r*4 + c)
-    double* T2 = LB;
+    // scratch blocks: the slot's SCR, or (chunk-parallel) a private pair behind the tall matrices of all chunks in PB
+    double* S0 = Q.par_chunks ? PB + (size_t)gridDim.y * tall + (size_t)chunk * 32 * TILE_ELEMS : SCR;
+    double* S1 = S0 + 16 * TILE_ELEMS;
+    double* T1 = PB + (size_t)chunk * tall;   // tall tile matrices: tile (r, c) at (r*4 + c)
+    double* T2 = LB + (size_t)chunk * tall;
     const Opnd opL = opnd_packed(LC, ACC_ROWK, LCe);
     const Opnd opR = opnd_packed(RX, ACC_ROWK);
     Acc acc;
@@ -755,6 +764,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
         const Opnd opMat = pass == 0 ? opL : opR;
         const Opnd opPrev = opnd_block(Tout, ACC_COLK, 0, 0, 0);
         for (int I = 0; I < nM; ++I) {
+            if (pass == 1 && Q.rx_inverse) {   // tmp2 block row I = sum_{J <= I} R^-1[I][J] tmp1[J]
+                acc_zero(acc);
+                gemm_macro(acc, pipe, opR, TPM * I, opnd_block(T1, ACC_COLK, 0, 0, 0), 0, 0, TPM * I + TPM, nullptr);
+                acc_foreach(acc, I, 0, [&](int it, int jt, int i, int j, double v0, double v1) {
+                    tile_store2(Tout + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j, v0, v1);
+                });
+                __syncthreads();
+                continue;
+            }
             acc_zero(acc);
             gemm_macro(acc, pipe, opMat, TPM * I, opPrev, 0, 0, TPM * I, nullptr);
             __syncthreads();
@@ -766,8 +784,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
                     s0 = s1 = 0.0;
                     if (gi < M) {
                         const int ci = gi / 3, fi = gi - 3 * ci + 1;
-                        if (s < T) s0 = kpair(P, P.t[ci], fi, Q.Xnew[2 * s], (int)Q.Xnew[2 * s + 1], ell, kvar, kinv, b);
-                        if (s + 1 < T) s1 = kpair(P, P.t[ci], fi, Q.Xnew[2 * s + 2], (int)Q.Xnew[2 * s + 3], ell, kvar, kinv, b);
+                        if (s < T) s0 = kpair(P, P.t[ci], fi, Xn[2 * s], (int)Xn[2 * s + 1], ell, kvar, kinv, b);
+                        if (s + 1 < T) s1 = kpair(P, P.t[ci], fi, Xn[2 * s + 2], (int)Xn[2 * s + 3], ell, kvar, kinv, b);
                     }
                 } else {
                     const double2 p = tile_load2(T1 + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j);
@@ -828,7 +846,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
             if (tid < 128 && s < T) {
                 double r = 0.0;
                 for (int w = 0; w < GEMM_THREADS / 128; ++w) r += red[tid + 128 * w];
-                Q.mean[((size_t)slot * Q.Ttot + Q.s0 + s) * D + d0] = r;
+                Q.mean[((size_t)slot * Q.Ttot + qs0 + s) * D + d0] = r;
             }
         }
         __syncthreads();
@@ -837,7 +855,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
         if (!Q.full_cov && tid < 128 && s < T) {
             double r = kvar + P.square_noise;
             for (int w = 0; w < GEMM_THREADS / 128; ++w) r += red[tid + 128 * w];
-            Q.var[(size_t)slot * Q.Ttot + Q.s0 + s] = r;
+            Q.var[(size_t)slot * Q.Ttot + qs0 + s] = r;
         }
     }
     if (Q.full_cov) {
@@ -854,12 +872,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
             const int s = it * TS + i, r = jt * TS + j;
             const double2 g2 = tile_load2(S0 + (size_t)(it * TPM + jt) * TILE_ELEMS, i, j);
             if (s < T && r < T) {
-                double k = kpair(P, Q.Xnew[2 * s], (int)Q.Xnew[2 * s + 1], Q.Xnew[2 * r], (int)Q.Xnew[2 * r + 1], ell, kvar, kinv, b);
+                double k = kpair(P, Xn[2 * s], (int)Xn[2 * s + 1], Xn[2 * r], (int)Xn[2 * r + 1], ell, kvar, kinv, b);
                 if (s == r) k += P.square_noise;
                 Q.var[((size_t)slot * T + s) * T + r] = k + g2.x - v0;
             }
             if (s < T && r + 1 < T) {
-                double k = kpair(P, Q.Xnew[2 * s], (int)Q.Xnew[2 * s + 1], Q.Xnew[2 * r + 2], (int)Q.Xnew[2 * r + 3], ell, kvar, kinv, b);
+                double k = kpair(P, Xn[2 * s], (int)Xn[2 * s + 1], Xn[2 * r + 2], (int)Xn[2 * r + 3], ell, kvar, kinv, b);
                 if (s == r + 1) k += P.square_noise;
                 Q.var[((size_t)slot * T + s) * T + r + 1] = k + g2.y - v1;
             }
@@ -868,9 +886,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
 }
 
 void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, int T, int Ttot, int s0, int full_cov, double* mean,
-                          double* var, cudaStream_t st) {
-    PredictArgs Q{Xnew, T, Ttot, s0, full_cov, mean, var};
+                          double* var, cudaStream_t st, int rx_inverse) {
+    PredictArgs Q{Xnew, T, Ttot, s0, full_cov, rx_inverse, 0, 0, mean, var};
     k_predict<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
+}
+
+// Marginal predictions of `nitems` slots (P.slot_map) at their own Ttot test inputs (Xnew + slot * xnew_stride) from the state
+// left by a bound + gradient evaluation.  Chunks of 128 inputs run as separate CTAs when their scratch fits into PB.
+void dense_launch_predict_slots(const DenseParams& P, int nitems, const double* Xnew, long long xnew_stride, int Ttot, double* mean,
+                                double* var, cudaStream_t st) {
+    const int chunks = (Ttot + MB - 1) / MB;
+    const long long need = (long long)chunks * ((long long)P.d.nT * TPM + 32) * TILE_ELEMS;
+    if (need <= P.d.mat_elems) {
+        PredictArgs Q{Xnew, 0, Ttot, 0, 0, 1, xnew_stride, 1, mean, var};
+        k_predict<<<dim3(nitems, chunks), GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
+    } else {
+        for (int s0 = 0; s0 < Ttot; s0 += MB) {
+            PredictArgs Q{Xnew + 2 * (size_t)s0, (Ttot - s0 < MB) ? (Ttot - s0) : MB, Ttot, s0, 0, 1, xnew_stride, 0, mean, var};
+            k_predict<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ debug: unpack a tile matrix to row-major

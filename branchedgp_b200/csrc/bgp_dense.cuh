@@ -49,6 +49,7 @@ struct DenseParams {
     double square_noise;      // White(1e-6) summand / MBGP noise_level on the square kernel
     double kl_weight;         // 1 (BGP) or D (MBGP single-b, MBGP/assigngp.py:637)
     int item0;                // slot s of this wave is item item0 + s
+    const int* slot_map;      // optional: CTA c works on slot slot_map[c] (subset launches of the batched fit); nullptr = identity
     long long slot_stride;    // doubles between consecutive slots, common to every per-slot array below
     // inputs (device)
     const double* t;          // [N]

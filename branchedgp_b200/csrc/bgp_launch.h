@@ -10,7 +10,9 @@ void dense_launch_prep(const DenseParams& P, const double* Apart, const double* 
                        const int* item_gene, int nitems, cudaStream_t st);
 void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_t st);
 void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, int T, int Ttot, int s0, int full_cov, double* mean,
-                          double* var, cudaStream_t st);
+                          double* var, cudaStream_t st, int rx_inverse = 0);
+void dense_launch_predict_slots(const DenseParams& P, int nitems, const double* Xnew, long long xnew_stride, int Ttot, double* mean,
+                                double* var, cudaStream_t st);
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st);
 cudaError_t sparse_init_kernels();
 void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* sub_out, cudaStream_t st);

@@ -116,6 +116,49 @@ int bgp_sparse_predict_host(bgp_handle* h, int N, int Dtot, int Mz, const double
  * HOST pointers. */
 int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi);
 
+/* ---- batched fitting ---------------------------------------------------------------------------------------------
+ * Replaces, for `count` work items at once, the optimiser loop of FitBranchingModel.FitModel (FitBranchingModel.py:96-140):
+ *   m.UpdateBranchingPoint(b, phiInitial); gpflow.optimizers.Scipy().minimize(m.training_loss, m.trainable_variables,
+ *   options=dict(maxiter=maxiter)); ll = m.log_posterior_density(); Phi = m.GetPhi(); predictBranchingModel(m)
+ * with logPhi, its gradient and the L-BFGS history resident on the GPU (bgp_fit.cu).  The optimiser restates SciPy's
+ * L-BFGS-B (unbounded) and its More'-Thuente line search; defaults below are SciPy's. */
+typedef struct bgp_fit_options {
+    int maxiter;            /* L-BFGS iterations per item (FitModel's maxiter, default 100) */
+    int maxcor;             /* stored correction pairs, <= 16 (SciPy maxcor = 10) */
+    int maxls;              /* evaluations per line search (20) */
+    int maxfun;             /* evaluations per item (15000) */
+    double ftol;            /* stop when (f_k - f_{k+1}) / max(|f_k|, |f_{k+1}|, 1) <= ftol (2.22e-9) */
+    double gtol;            /* stop when max |g| <= gtol (1e-5) */
+    int train_hyp;          /* 1: lengthscale, kernel variance and likelihood variance are optimised with logPhi (softplus
+                               transforms, GPflow positive()); 0: FitModel(fixHyperparameters=True) */
+    int has_prior[3];       /* Normal priors on the constrained (lengthscale, kernel variance, likelihood variance) */
+    double prior_mean[3];
+    double prior_sd[3];
+    int max_slots;          /* items fitted concurrently; 0 = one per SM, reduced to what fits in device memory */
+} bgp_fit_options;
+
+void bgp_fit_default_options(bgp_fit_options* o);
+
+/* Dense AssignGP (FitModel(M=0)).  HOST pointers.
+ *   t[N], Y[nY][N][D], item_gene[count], b[count], prior = phiPrior[N][2], phiInitial[N][2] (InitialiseVariationalPhi,
+ *   assigngp_dense.py:92-128, is evaluated on the device per item), hyp0[count][3] initial constrained hyper-parameters;
+ *   Xnew[count][T][2] test inputs per item (T = 0: no prediction).
+ * outputs per item: objective = log posterior density at the optimum (FitModel's loglik entry), elbo (the bound alone),
+ *   hyp[3], phi[N][3] (GetPhi), pred_mean[T][D], pred_var[T] (predict_f), iters, nfev,
+ *   status: 0 converged (gradient), 1 converged (function decrease), 2 maxiter, 3 maxfun, 4 abnormal line search,
+ *           5 a Cholesky factorisation failed (objective = NaN, like FitModel's exception branch);
+ *   logPhi_out[count][N][3N] optional (NULL to skip). */
+int bgp_dense_fit_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY, const int* item_gene,
+                       const double* b, const double* prior, const double* phiInitial, const double* hyp0, int kernel_kind,
+                       const bgp_fit_options* opt, int T, const double* Xnew, double* objective, double* elbo, double* hyp,
+                       double* phi, double* pred_mean, double* pred_var, int* iters, int* nfev, int* status, double* logPhi_out);
+/* Same for AssignGPSparse (FitModel(M>0)) with inducing inputs Z[Mz][2]. */
+int bgp_sparse_fit_host(bgp_handle* h, int count, int N, int D, int Mz, const double* t, const double* Z, const double* Y, int nY,
+                        const int* item_gene, const double* b, const double* prior, const double* phiInitial, const double* hyp0,
+                        int kernel_kind, const bgp_fit_options* opt, int T, const double* Xnew, double* objective, double* elbo,
+                        double* hyp, double* phi, double* pred_mean, double* pred_var, int* iters, int* nfev, int* status,
+                        double* logPhi_out);
+
 /* Per-kernel device timing (CUDA events recorded on the caller's stream around every launch).  Phase ids:
  * 0 phi forward, 1 prep, 2 chol K, 3 P = L^T D L + I, 4 chol P, 5 solves, 6 trtri, 7 lauum, 8 trmm, 9 post, 10 adjoint,
  * 11 phi backward.  bgp_profile_read waits for the recorded events, accumulates milliseconds per phase since the last
@@ -134,6 +177,12 @@ int bgp_debug_padded_size(int N);
 int bgp_debug_dense_matrix(bgp_handle* h, int slot, int which, int symmetric, double* out_host);
 /* which: 0 A, 1 Delta, 2 v, 3 z, 4 c, 5 q, 6 vbar, 7 delta, 8 Abar; out_host[len] (len = Mp or D*Mp) */
 int bgp_debug_dense_vector(bgp_handle* h, int slot, int which, double* out_host);
+
+/* Host-only hooks for the optimiser pieces of bgp_fit.cu (no GPU needed): one More'-Thuente line-search call on caller-owned
+ * state[32] (returns 0 evaluate at *stp, 1 convergence, 2 warning, 3 error), and the limited-memory direction d = -H g
+ * computed from inner products of S[col][n], Y[col][n] (oldest pair first) and g[n]. */
+int bgp_debug_linesearch(double* state, int start, double* stp, double f, double g);
+int bgp_debug_lbfgs_direction(int col, int n, const double* S, const double* Y, const double* g, double* d);
 
 #ifdef __cplusplus
 }

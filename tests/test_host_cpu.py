@@ -88,3 +88,68 @@ def test_parameter_transforms_and_kernel_container():
     assert np.allclose(K, bgp_numpy.branch_K(X, X, 0.4, 1.7, 1.0, 0), rtol=1e-13)
     n = gpflow.Normal(2.0, 1.0)
     assert np.isclose(n.log_prob(2.0), -0.5 * np.log(2 * np.pi))
+
+
+def test_linesearch_hook_matches_scipy_dcsrch():
+    """The More'-Thuente line search of the batched fit (bgp_fit.cu) visits the same trial steps as SciPy's DCSRCH."""
+    import ctypes
+    from scipy.optimize._dcsrch import DCSRCH
+    from branchedgp_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(1)
+    checked = 0
+    for _ in range(60):
+        a, b, c, e = rng.standard_normal(4)
+
+        def phi(x):
+            return -abs(a) * x + (abs(b) + 0.1) * x * x + 0.3 * c * np.sin(3 * x) * x * x + 0.05 * e * x ** 3 * np.cos(x)
+
+        def dphi(x):
+            return (-abs(a) + 2 * (abs(b) + 0.1) * x + 0.3 * c * (3 * np.cos(3 * x) * x * x + 2 * x * np.sin(3 * x))
+                    + 0.05 * e * (3 * x * x * np.cos(x) - x ** 3 * np.sin(x)))
+        if dphi(0.0) >= 0:
+            continue
+        stp0 = float(rng.choice([1.0, 0.1, 5.0, 1e-3]))
+        ref_trace = []
+
+        def phi_logged(x):
+            ref_trace.append(x)
+            return phi(x)
+        DCSRCH(phi_logged, dphi, 1e-3, 0.9, 0.1, 0.0, 1e10)(stp0, phi0=phi(0.0), derphi0=dphi(0.0), maxiter=30)
+        state = np.zeros(32)
+        stp = ctypes.c_double(stp0)
+        task = lib.bgp_debug_linesearch(state.ctypes.data, 1, ctypes.byref(stp), phi(0.0), dphi(0.0))
+        trace = []
+        while task == 0 and len(trace) < 30:
+            trace.append(stp.value)
+            task = lib.bgp_debug_linesearch(state.ctypes.data, 0, ctypes.byref(stp), phi(stp.value), dphi(stp.value))
+        assert len(trace) == len(ref_trace)
+        np.testing.assert_allclose(trace, ref_trace, rtol=1e-13)
+        checked += 1
+    assert checked > 20
+
+
+def test_direction_hook_is_the_two_loop_recursion():
+    from branchedgp_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(0)
+    n = 60
+    A = rng.standard_normal((n, n))
+    H = A @ A.T + n * np.eye(n)
+    for col in (0, 1, 4, 10):
+        S = rng.standard_normal((max(col, 1), n))
+        Y = S @ H
+        g = rng.standard_normal(n)
+        d = np.empty(n)
+        assert lib.bgp_debug_lbfgs_direction(col, n, S.ctypes.data, Y.ctypes.data, g.ctypes.data, d.ctypes.data) == 0
+        q = g.copy()
+        alphas = []
+        for s, y in zip(S[:col][::-1], Y[:col][::-1]):
+            al = (s @ q) / (s @ y)
+            q -= al * y
+            alphas.append(al)
+        if col:
+            q *= (S[col - 1] @ Y[col - 1]) / (Y[col - 1] @ Y[col - 1])
+        for (s, y), al in zip(zip(S[:col], Y[:col]), alphas[::-1]):
+            q += (al - (y @ q) / (s @ y)) * s
+        np.testing.assert_allclose(d, -q, rtol=1e-10, atol=1e-14)
