@@ -18,7 +18,10 @@ import sys
 import threading
 import time
 
-import numpy as np
+# bgp_dense_elbo_grad_host keeps up to 16 item groups in flight on their own streams (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

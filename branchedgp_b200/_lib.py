@@ -66,6 +66,7 @@ SIGNATURES = {
                            + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 11),
     "bgp_sparse_fit_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
                             + [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 11),
+    "bgp_debug_gemm_timers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "bgp_debug_linesearch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double]),
     "bgp_debug_lbfgs_direction": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -107,6 +108,9 @@ def load_library():
     with _lib_lock:
         if _lib is not None:
             return _lib
+        # the host-pointer entry points keep up to 16 item groups in flight on their own streams; the default of 8 hardware
+        # work queues would serialise some of them (only effective if the CUDA context does not exist yet)
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         path = library_path()
         if not os.path.exists(path):
             raise BgpError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -247,8 +247,8 @@ int ensure_stage(bgp_handle* h, size_t bytes) {
 }
 extern "C" {
 
-// Host-pointer entry.  The items are cut into groups of about a quarter of the SMs; each group owns a lane (CUDA stream +
-// workspace slots + staging buffers) on which its H2D copy, kernels and D2H copy are queued in order.  Up to four groups
+// Host-pointer entry.  The items are cut into groups of about an eighth of the SMs; each group owns a lane (CUDA stream +
+// workspace slots + staging buffers) on which its H2D copy, kernels and D2H copy are queued in order.  Up to eight groups
 // compute concurrently (their one-CTA-per-item kernels share the SMs) while the copy engines move the next / previous
 // groups, so for calls with more than one SM-count of items the PCIe time hides behind the arithmetic.
 int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
@@ -264,13 +264,15 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
     const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
     const SlotLayout SL = slot_layout(make_dims(N, D));
     const size_t per_item = (size_t)N * M * 8;
-    const int conc = 4;
+    int conc = 8;   // measured on B200 (tools/e2e_sweep.sh, 296 items at N = 1000): 4 groups / 8 lanes 278 items/s, 8 / 16 296, 16 / 20 262
     int sm_cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
     if (sm_cap > count) sm_cap = count;
+    if (const char* e = getenv("BGP_HOST_CONC")) conc = atoi(e) > 0 ? atoi(e) : conc;
     int gs = (sm_cap + conc - 1) / conc;                 // items per group
     if (gs < 1) gs = 1;
     int ngroups = (count + gs - 1) / gs;
     int lanes = ngroups < 2 * conc ? ngroups : 2 * conc;
+    if (const char* e = getenv("BGP_HOST_LANES")) { const int l_ = atoi(e); if (l_ > 0) lanes = l_ < ngroups ? l_ : ngroups; }
     // per-lane staging: per-item inputs, outputs, logPhi and gradient
     size_t lo = 0;
     auto ltake = [&](size_t bytes) { size_t r = lo; lo = align_up(lo + bytes, 256); return r; };
@@ -642,6 +644,14 @@ int bgp_debug_dense_matrix(bgp_handle* h, int slot, int which, int symmetric, do
     cudaError_t e = cudaMemcpy(out_host, tmp, n * 8, cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(h, BGP_ERR_CUDA, "debug copy: %s", cudaGetErrorString(e));
+    return BGP_OK;
+}
+
+int bgp_debug_gemm_timers(bgp_handle* h, unsigned long long* out8, int reset) {
+    if (!h || !out8) return BGP_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    dense_read_gemm_timers(out8, reset);
     return BGP_OK;
 }
 

@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_lauum(DenseParams P) {
                 tile_store2(PB + packed_tile(it, jt) * TILE_ELEMS, i, j, -hD * v0 - 0.5 * qq0, -hD * v1 - 0.5 * qq1);
             });
         }
+    pipe_report(pipe);
 }
 
 // ------------------------------------------------------------------------------------------------ k_trmm:  G = L Pbar (lower), Lbar, delta partials
@@ -962,6 +963,17 @@ void dense_launch_phase(const DenseParams& P, int nitems, int phase, cudaStream_
         case 9: k_adj<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P); break;
         default: break;
     }
+}
+
+// Cycle counters of the tile GEMM pipeline (only a BGP_TIMING build fills them; tools/gemm_timers.py).
+void dense_read_gemm_timers(unsigned long long* out8, int reset) {
+#ifdef BGP_TIMING
+    cudaMemcpyFromSymbol(out8, g_gemm_timers, 8 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_gemm_timers, z, sizeof(z)); }
+#else
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    (void)reset;
+#endif
 }
 
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st) {

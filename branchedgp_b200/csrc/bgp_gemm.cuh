@@ -13,6 +13,9 @@
 #ifndef BGP_KUNROLL
 #define BGP_KUNROLL 2
 #endif
+#ifndef BGP_SWPIPE
+#define BGP_SWPIPE 0
+#endif
 
 namespace bgp {
 
@@ -65,13 +68,40 @@ struct Pipe {
     uint64_t* full;    // NSTAGES mbarriers: TMA bytes of the stage have landed
     uint64_t* empty;   // NSTAGES mbarriers: all 8 warps are done reading the stage
     uint32_t it;       // running k-step counter; identical in every thread of the CTA
+#ifdef BGP_TIMING
+    long long t_first, t_steady, t_empty, t_macro, n_calls, n_ksteps;   // cycle counters of the calling thread (tools/gemm_timers.py)
+#endif
 };
+
+#ifdef BGP_TIMING
+__device__ unsigned long long g_gemm_timers[8];
+#define BGP_TIC() const long long tic_ = clock64()
+#define BGP_TOC(field) pipe.field += clock64() - tic_
+// warp 0 lane 0 reports the consumer-side waits, the producer thread the empty-barrier waits
+__device__ __forceinline__ void pipe_report(const Pipe& p) {
+    if (threadIdx.x == 0) {
+        atomicAdd(&g_gemm_timers[0], (unsigned long long)p.t_first);
+        atomicAdd(&g_gemm_timers[1], (unsigned long long)p.t_steady);
+        atomicAdd(&g_gemm_timers[3], (unsigned long long)p.t_macro);
+        atomicAdd(&g_gemm_timers[4], (unsigned long long)p.n_calls);
+        atomicAdd(&g_gemm_timers[5], (unsigned long long)p.n_ksteps);
+    }
+    if (threadIdx.x == GEMM_THREADS - 32) atomicAdd(&g_gemm_timers[2], (unsigned long long)p.t_empty);
+}
+#else
+#define BGP_TIC()
+#define BGP_TOC(field)
+__device__ __forceinline__ void pipe_report(const Pipe&) {}
+#endif
 
 __device__ __forceinline__ void pipe_init(Pipe& p, unsigned char* smem) {
     p.stages = reinterpret_cast<double*>(smem);
     p.full = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES + SMEM_RED_DOUBLES * 8);
     p.empty = p.full + NSTAGES;
     p.it = 0;
+#ifdef BGP_TIMING
+    p.t_first = p.t_steady = p.t_empty = p.t_macro = p.n_calls = p.n_ksteps = 0;
+#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGES; ++s) { mbar_init(p.full + s, 1); mbar_init(p.empty + s, GEMM_WARPS); }
         fence_mbar_init();
@@ -107,9 +137,7 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
 #pragma unroll
     for (int o8 = 0; o8 < 4; ++o8) toff[o8] = tbase + ((8 * o8 + g) ^ c2);
     const bool h0 = FULL || (nmask & 1), h1 = (NBT == 2) && (FULL || (nmask & 2));
-#pragma unroll KUNROLL
-    for (int k4 = 0; k4 < 8; ++k4) {
-        double af[4], bf[NI];
+    auto load = [&](int k4, double (&af)[4], double (&bf)[NI]) {
         const int kx = ((4 * k4) ^ g3);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) af[mi] = As[TA ? (toff[mi] + 4 * k4 * TS) : (nbase + 8 * mi * TS + kx)];
@@ -126,6 +154,8 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
             if (FULL) bf[ni] = Bt[off];
             else bf[ni] = ((ni >> 2) ? h1 : h0) ? Bt[off] : 0.0;
         }
+    };
+    auto mma = [&](const double (&af)[4], const double (&bf)[NI]) {
         if (h0) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
@@ -138,7 +168,28 @@ __device__ __forceinline__ void warp_kstep(Acc& acc, const double* __restrict__ 
 #pragma unroll
                 for (int ni = 4; ni < NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
+    };
+#if BGP_SWPIPE
+    // Experiment kept for reference (off): software pipelining over the back edge -- fragments of k4+1 / k4+2 requested before
+    // the MMAs of k4 / k4+1.  Measured on B200: 8911 cycles per k-step against 8623 for the plain loop (tools/gemm_timers.py;
+    // small spills, and the LDS wait was never the limiter), so the plain loop below is the shipped one.
+    double a0[4], b0[NI], a1[4], b1[NI];
+    load(0, a0, b0);
+#pragma unroll 1
+    for (int k4 = 0; k4 < 8; k4 += 2) {
+        load(k4 + 1, a1, b1);
+        mma(a0, b0);
+        load((k4 + 2) & 7, a0, b0);   // the wrap on the last trip re-reads k4 = 0 (unused) instead of branching
+        mma(a1, b1);
     }
+#else
+#pragma unroll KUNROLL
+    for (int k4 = 0; k4 < 8; ++k4) {
+        double af[4], bf[NI];
+        load(k4, af, bf);
+        mma(af, bf);
+    }
+#endif
 }
 
 template <bool FULL>
@@ -181,6 +232,10 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
     // first and the refill is requested as early as the ring allows (with warp 0 as producer the loads were issued by the
     // slowest warp and every other warp then waited for the data: ncu long_scoreboard 17 % on the full-barrier spin).
     __syncthreads();   // every warp is done with the ring (previous GEMM or scratch use)
+#ifdef BGP_TIMING
+    const long long t_macro0 = clock64();
+    pipe.n_calls += 1; pipe.n_ksteps += nk;
+#endif
     if (tid == PRODUCER_TID) {
         const int pre = nk < (NSTAGES - 1) ? nk : (NSTAGES - 1);
         for (int p = 0; p < pre; ++p) {
@@ -193,13 +248,17 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
         if (ks + NSTAGES - 1 < nk) {
             if (tid == PRODUCER_TID) {   // refill the slot released NSTAGES-1 k-steps ago once all 8 warps have arrived on its `empty` barrier
                 const uint32_t itn = pipe.it + (uint32_t)(ks + NSTAGES - 1);
-                if (itn >= NSTAGES) mbar_wait(pipe.empty + itn % NSTAGES, ((itn / NSTAGES) - 1u) & 1u);
+                { BGP_TIC(); if (itn >= NSTAGES) mbar_wait(pipe.empty + itn % NSTAGES, ((itn / NSTAGES) - 1u) & 1u); BGP_TOC(t_empty); }
                 issue(ks + NSTAGES - 1);
             }
         }
         const uint32_t it = pipe.it + (uint32_t)ks;
         const int st = (int)(it % NSTAGES);
+#ifdef BGP_TIMING
+        { BGP_TIC(); mbar_wait(pipe.full + st, (it / NSTAGES) & 1u); if (ks < NSTAGES - 1) { BGP_TOC(t_first); } else { BGP_TOC(t_steady); } }
+#else
         mbar_wait(pipe.full + st, (it / NSTAGES) & 1u);
+#endif
         const int kt = kt0 + ks;
         bool ta, tb0, tb1;
         const double* pa = resolve(A, ao0 + wa, kt, ta);
@@ -225,6 +284,9 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
         if (lane == 0) mbar_arrive(pipe.empty + st);
     }
     pipe.it += (uint32_t)nk;
+#ifdef BGP_TIMING
+    pipe.t_macro += clock64() - t_macro0;
+#endif
 }
 
 // Visit every accumulator pair of the calling thread: f(tile_row, tile_col, i_in_tile, j_in_tile (even), v0, v1)

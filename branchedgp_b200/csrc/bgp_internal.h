@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 

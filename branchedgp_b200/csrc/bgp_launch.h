@@ -13,6 +13,7 @@ void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, 
                           double* var, cudaStream_t st, int rx_inverse = 0);
 void dense_launch_predict_slots(const DenseParams& P, int nitems, const double* Xnew, long long xnew_stride, int Ttot, double* mean,
                                 double* var, cudaStream_t st);
+void dense_read_gemm_timers(unsigned long long* out8, int reset);
 void dense_unpack(const double* packed, double* out, int Mp, int symmetric, cudaStream_t st);
 cudaError_t sparse_init_kernels();
 void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* sub_out, cudaStream_t st);

@@ -178,6 +178,11 @@ int bgp_debug_dense_matrix(bgp_handle* h, int slot, int which, int symmetric, do
 /* which: 0 A, 1 Delta, 2 v, 3 z, 4 c, 5 q, 6 vbar, 7 delta, 8 Abar; out_host[len] (len = Mp or D*Mp) */
 int bgp_debug_dense_vector(bgp_handle* h, int slot, int which, double* out_host);
 
+/* Cycle counters of the tile GEMM pipeline in k_lauum, filled only by a -DBGP_TIMING build (make timing; tools/gemm_timers.py):
+ * [0] cycles a consumer warp waited for the first stages of a GEMM call, [1] for later stages, [2] producer waits for a free
+ * stage, [3] cycles inside the GEMM calls, [4] calls, [5] k-steps; summed over CTAs. */
+int bgp_debug_gemm_timers(bgp_handle* h, unsigned long long* out8, int reset);
+
 /* Host-only hooks for the optimiser pieces of bgp_fit.cu (no GPU needed): one More'-Thuente line-search call on caller-owned
  * state[32] (returns 0 evaluate at *stp, 1 convergence, 2 warning, 3 error), and the limited-memory direction d = -H g
  * computed from inner products of S[col][n], Y[col][n] (oldest pair first) and g[n]. */
