@@ -256,10 +256,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
             fence_proxy_async();
             // X = C * inv(L_JJ)^T, in place
             acc_zero(acc);
-            gemm_macro(acc, pipe, opL, TPM * I, opInv, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            gemm_macro(acc, pipe, opL, TPM * I, opInv, TPM * J, TPM * J, TPM * J + TPM, nullptr, 0);   // the skipped operand is B
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 tile_store2(dst + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
-            });
+            }, 0);
             fence_proxy_async();
         }
     }
@@ -428,10 +428,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri(DenseParams P) {
             fence_proxy_async();
             // X[I,J] = -acc * inv(R_JJ)
             acc_zero(acc);
-            gemm_macro(acc, pipe, opRow, TPM * I, opInv, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            gemm_macro(acc, pipe, opRow, TPM * I, opInv, TPM * J, TPM * J, TPM * J + TPM, nullptr, 0);   // the skipped operand is B
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 tile_store2(RX + packed_tile(it, jt) * TILE_ELEMS, i, j, -v0, -v1);
-            });
+            }, 0);
             fence_proxy_async();
         }
         // X[J,J] = inv(R_JJ)
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
                 double r = rs[mi];
                 r += __shfl_xor_sync(0xffffffffu, r, 1);
                 r += __shfl_xor_sync(0xffffffffu, r, 2);
-                if (c == 0) red[(warp >> 2) * MB + (warp & 3) * TS + 8 * mi + g] = r;   // one partial per column group of warps
+                if (c == 0) red[warp_col_group(warp) * MB + warp_row_tile(warp) * TS + 8 * mi + g] = r;   // one partial per column group of warps
             }
             __syncthreads();
             if (tid < MB) {
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
             fence_proxy_async();
             // Atilde[I,J] = E inv(L_JJ)
             acc_zero(acc);
-            gemm_macro(acc, pipe, opArow, TPM * I, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            gemm_macro(acc, pipe, opArow, TPM * I, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr, 0);   // the skipped operand is B
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 tile_store2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
                 if (want_hyp) {
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
                     hyper_accum(P, ka, dkal, dkab, KT, gi, gj, v0, kvar, kinv, gl, gv, gb);
                     hyper_accum(P, ka, dkal, dkab, KT, gi, gj + 1, v1, kvar, kinv, gl, gv, gb);
                 }
-            });
+            }, 0);
             fence_proxy_async();
         }
         // ---- diagonal block:  Leff = tril(Lbar_JJ) - tril(sum_{I>J} Atilde[I,J]^T Lc[I,J])
@@ -685,11 +685,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
         fence_proxy_async();
         // S = V inv(L_JJ)
         acc_zero(acc);
-        gemm_macro(acc, pipe, opnd_block(S0, ACC_ROWK, TPM * J, TPM * J, 0), TPM * J, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr);
+        gemm_macro(acc, pipe, opnd_block(S0, ACC_ROWK, TPM * J, TPM * J, 0), TPM * J, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr, 0);
         acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
             const int a = it - TPM * J, b = jt - TPM * J;
             tile_store2(S1 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, v0, v1);
-        });
+        }, 0);
         __syncthreads();
         // Atilde_JJ = S + S^T  (diagonal tiles stored fully symmetric)
         for (int a = 0; a < TPM; ++a)

@@ -25,6 +25,23 @@ constexpr int KUNROLL = BGP_KUNROLL;
 #endif
 constexpr int PRODUCER_TID = BGP_PRODUCER_LAST ? (GEMM_THREADS - 32) : 0;   // unroll factor of the k4 loop of warp_kstep
 
+// Warp -> 32x32 warp tile of the 128x128 macro tile.  Warp w runs on SM sub-partition w & 3.  Every structural-zero skip
+// of the dense pipeline is on the A (row) operand (triangular factors in syrk / trtri / lauum / trmm), so the four warps
+// that share an A tile row are spread over the four sub-partitions: a skipped row tile then frees one warp's share of the
+// DMMA pipe on each of them instead of idling one sub-partition while the others still run four warps.
+#ifndef BGP_ROWS_ACROSS_SMSP
+#define BGP_ROWS_ACROSS_SMSP 1
+#endif
+// rowmap = 1 (default): A tile rows across sub-partitions; rowmap = 0: B tile columns across sub-partitions, for the calls whose
+// skipped operand is B (multiplications by an inverse diagonal block from the right).  gemm_macro and the acc_foreach that
+// reads its accumulators must be given the same value.
+__device__ __forceinline__ int warp_row_tile(int warp, int rowmap = 1) {
+    return (BGP_ROWS_ACROSS_SMSP && WCOLS == 4 && rowmap) ? (warp >> 2) : (warp & 3);
+}
+__device__ __forceinline__ int warp_col_group(int warp, int rowmap = 1) {
+    return (BGP_ROWS_ACROSS_SMSP && WCOLS == 4 && rowmap) ? (warp & 3) : (warp >> 2);
+}
+
 enum { ACC_ROWK = 0, ACC_COLK = 1, ACC_SYM = 2 };
 enum { LAY_PACKED = 0, LAY_BLOCK = 1 };
 
@@ -202,12 +219,12 @@ __device__ __forceinline__ void warp_kstep_dispatch(Acc& acc, bool ta, bool tb, 
 // acc += Aop[ao0*32 .. +128][kt0*32 .. kt1*32) * Bop[bo0*32 .. +128][same k]^T, optionally with the k index scaled
 // by kscale[k].  Must be called by all GEMM_THREADS threads with identical arguments.
 __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, int ao0, const Opnd& B, int bo0, int kt0,
-                                           int kt1, const double* __restrict__ kscale) {
+                                           int kt1, const double* __restrict__ kscale, int rowmap = 1) {
     const int nk = kt1 - kt0;
     if (nk <= 0) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
-    const int wa = warp & 3, wb = (warp >> 2) * NBT;
+    const int wa = warp_row_tile(warp, rowmap), wb = warp_col_group(warp, rowmap) * NBT;
 
     auto issue = [&](int ks) {
         const uint32_t it = pipe.it + (uint32_t)ks;
@@ -292,10 +309,10 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
 // Visit every accumulator pair of the calling thread: f(tile_row, tile_col, i_in_tile, j_in_tile (even), v0, v1)
 // for elements (i, j) and (i, j+1) of tile (4*I + ..., 4*J + ...).
 template <class F>
-__device__ __forceinline__ void acc_foreach(Acc& acc, int I, int J, F f) {
+__device__ __forceinline__ void acc_foreach(Acc& acc, int I, int J, F f, int rowmap = 1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, c = lane & 3;
-    const int wa = warp & 3, wb = (warp >> 2) * NBT;
+    const int wa = warp_row_tile(warp, rowmap), wb = warp_col_group(warp, rowmap) * NBT;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
