@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
+    pipe.row_limit = dm.nTv;   // tile rows beyond the last one that holds a row < M are identity padding
     double* red = smem_red(smem);
     double* Dm = pipe.stages;
     double* dst = SRC == 0 ? LC : RX;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
     for (int J = 0; J < nM; ++J) {
         // ---- diagonal macro block
         acc_zero(acc);
-        gemm_macro(acc, pipe, opL, TPM * J, opL, TPM * J, 0, TPM * J, nullptr);
+        gemm_macro(acc, pipe, opL, TPM * J, opL, TPM * J, 0, TPM * J, nullptr, 2);   // only the lower warp tiles
         __syncthreads();   // the ring doubles as the 128x128 scratch from here on
         acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
             if (it < jt) return;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol(DenseParams P) {
             double* o = Dm + (gi - MB * J) * DLD + (gj - MB * J);
             o[0] = s0 - v0;
             o[1] = s1 - v1;
-        });
+        }, 2);
         __syncthreads();
         chol128(Dm, fail, MB * J);
         if (SRC == 1) {
@@ -274,20 +275,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
+    pipe.row_limit = dm.nTv;   // tile rows beyond the last one that holds a row < M are identity padding
     const Opnd opL = opnd_packed(LC, ACC_COLK, LCe);
     const double* Delta = vec + VL.Delta;
     Acc acc;
     for (int I = 0; I < dm.nM; ++I)
         for (int J = 0; J <= I; ++J) {
             acc_zero(acc);
-            gemm_macro(acc, pipe, opL, TPM * I, opL, TPM * J, TPM * I, dm.nTv, Delta);
+            const int rowmap = (I == J) ? 2 : 1;
+            gemm_macro(acc, pipe, opL, TPM * I, opL, TPM * J, TPM * I, dm.nTv, Delta, rowmap);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 if (it < jt) return;
                 const int gi = it * TS + i, gj = jt * TS + j;
                 if (gi == gj) v0 += 1.0;
                 if (gi == gj + 1) v1 += 1.0;
                 tile_store2(RX + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
-            });
+            }, rowmap);
         }
 }
 
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
+    pipe.row_limit = dm.nTv;   // tile rows beyond the last one that holds a row < M are identity padding
     const int nM = dm.nM;
     const Opnd opRow = opnd_packed(RX, ACC_ROWK);
     const Opnd opCol = opnd_packed(RX, ACC_COLK);
@@ -452,6 +456,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_lauum(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
+    pipe.row_limit = dm.nTv;   // tile rows beyond the last one that holds a row < M are identity padding
     const Opnd opX = opnd_packed(RX, ACC_COLK);
     const double* q = vec + VL.q;
     const int Mp = dm.Mp, D = dm.D;
@@ -460,7 +465,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_lauum(DenseParams P) {
     for (int I = 0; I < dm.nM; ++I)
         for (int J = 0; J <= I; ++J) {
             acc_zero(acc);
-            gemm_macro(acc, pipe, opX, TPM * I, opX, TPM * J, TPM * I, dm.nTv, nullptr);
+            const int rowmap = (I == J) ? 2 : 1;
+            gemm_macro(acc, pipe, opX, TPM * I, opX, TPM * J, TPM * I, dm.nTv, nullptr, rowmap);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 if (it < jt) return;
                 const int gi = it * TS + i, gj = jt * TS + j;
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_lauum(DenseParams P) {
                     qq1 += qi * q[(size_t)d * Mp + gj + 1];
                 }
                 tile_store2(PB + packed_tile(it, jt) * TILE_ELEMS, i, j, -hD * v0 - 0.5 * qq0, -hD * v1 - 0.5 * qq1);
-            });
+            }, rowmap);
         }
     pipe_report(pipe);
 }
@@ -481,6 +487,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
+    pipe.row_limit = dm.nTv;   // tile rows beyond the last one that holds a row < M are identity padding
     double* red = smem_red(smem);
     const Opnd opL = opnd_packed(LC, ACC_ROWK, LCe);
     const Opnd opP = opnd_packed(PB, ACC_SYM);
@@ -494,7 +501,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
     for (int I = 0; I < dm.nM; ++I)
         for (int J = 0; J <= I; ++J) {
             acc_zero(acc);
-            gemm_macro(acc, pipe, opL, TPM * I, opP, TPM * J, 0, min(TPM * I + TPM, dm.nTv), nullptr);
+            const int rowmap = (I == J) ? 2 : 1;
+            gemm_macro(acc, pipe, opL, TPM * I, opP, TPM * J, 0, min(TPM * I + TPM, dm.nTv), nullptr, rowmap);
             double rs[4] = {0.0, 0.0, 0.0, 0.0};
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 if (it < jt) return;
@@ -513,15 +521,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trmm(DenseParams P) {
                 if (gi >= gj + 1) { o1 = dl * v1 + vz1 / likvar; r += v1 * l.y; }
                 rs[i >> 3] += r;
                 tile_store2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j, o0, o1);
-            });
+            }, rowmap);
             // delta partial of this macro tile: row sums over its 128 columns
+            if (rowmap == 2)   // upper warp tiles are not computed on diagonal macro tiles: their partials are zero
+                for (int e = tid; e < WCOLS * MB; e += GEMM_THREADS) red[e] = 0.0;
             __syncthreads();
+            {
+                int wa_, wb_;
+                bool idle_;
+                warp_tile(warp, rowmap, wa_, wb_, idle_);
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                double r = rs[mi];
-                r += __shfl_xor_sync(0xffffffffu, r, 1);
-                r += __shfl_xor_sync(0xffffffffu, r, 2);
-                if (c == 0) red[warp_col_group(warp) * MB + warp_row_tile(warp) * TS + 8 * mi + g] = r;   // one partial per column group of warps
+                for (int mi = 0; mi < 4; ++mi) {
+                    double r = rs[mi];
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    if (c == 0 && !idle_) red[wb_ * MB + wa_ * TS + 8 * mi + g] = r;   // one partial per column group of warps
+                }
             }
             __syncthreads();
             if (tid < MB) {
@@ -607,6 +622,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
     pipe_init(pipe, smem);
+    pipe.row_limit = dm.nTv;   // tile rows beyond the last one that holds a row < M are identity padding
     double* red = smem_red(smem);
     const int nM = dm.nM, nT = dm.nTv;   // k-ranges stop at the last tile that holds a row < M
     const double* ka = vec + VL.ka;

@@ -42,6 +42,23 @@ __device__ __forceinline__ int warp_col_group(int warp, int rowmap = 1) {
     return (BGP_ROWS_ACROSS_SMSP && WCOLS == 4 && rowmap) ? (warp & 3) : (warp >> 2);
 }
 
+// rowmap = 2: diagonal macro tiles whose upper triangle is never used.  Only the 10 lower warp tiles are computed, dealt
+// 3/3/2/2 over the sub-partitions (warp w sits on sub-partition w & 3), so such a tile costs 3/4 of a full one.
+//   warp:      0      1      2      3      4      5      6      7      8      9     10..15
+//   (wa, wb): (0,0)  (1,1)  (2,2)  (3,3)  (1,0)  (2,1)  (3,1)  (3,2)  (2,0)  (3,0)   idle
+__device__ __forceinline__ void warp_tile(int warp, int rowmap, int& wa, int& wb, bool& idle) {
+    idle = false;
+    if (rowmap == 2 && WCOLS == 4) {
+        const int a = (int)((0xFFFFFF3233213210ull >> (4 * warp)) & 15), b = (int)((0xFFFFFF0021103210ull >> (4 * warp)) & 15);
+        idle = (a == 15);
+        wa = idle ? 0 : a;
+        wb = idle ? 0 : b;
+    } else {
+        wa = warp_row_tile(warp, rowmap);
+        wb = warp_col_group(warp, rowmap);
+    }
+}
+
 enum { ACC_ROWK = 0, ACC_COLK = 1, ACC_SYM = 2 };
 enum { LAY_PACKED = 0, LAY_BLOCK = 1 };
 
@@ -85,6 +102,7 @@ struct Pipe {
     uint64_t* full;    // NSTAGES mbarriers: TMA bytes of the stage have landed
     uint64_t* empty;   // NSTAGES mbarriers: all 8 warps are done reading the stage
     uint32_t it;       // running k-step counter; identical in every thread of the CTA
+    int row_limit;     // A (= output) tile rows >= row_limit hold only identity padding: their warps skip the MMAs (accumulators stay 0)
 #ifdef BGP_TIMING
     long long t_first, t_steady, t_empty, t_macro, n_calls, n_ksteps;   // cycle counters of the calling thread (tools/gemm_timers.py)
 #endif
@@ -116,6 +134,7 @@ __device__ __forceinline__ void pipe_init(Pipe& p, unsigned char* smem) {
     p.full = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES + SMEM_RED_DOUBLES * 8);
     p.empty = p.full + NSTAGES;
     p.it = 0;
+    p.row_limit = 1 << 30;
 #ifdef BGP_TIMING
     p.t_first = p.t_steady = p.t_empty = p.t_macro = p.n_calls = p.n_ksteps = 0;
 #endif
@@ -224,7 +243,11 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
     if (nk <= 0) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
-    const int wa = warp_row_tile(warp, rowmap), wb = warp_col_group(warp, rowmap) * NBT;
+    int wa, wb;
+    bool idle;
+    warp_tile(warp, rowmap, wa, wb, idle);
+    wb *= NBT;
+    const bool row_pad = idle || (ao0 + wa >= pipe.row_limit);
 
     auto issue = [&](int ks) {
         const uint32_t it = pipe.it + (uint32_t)ks;
@@ -283,7 +306,7 @@ __device__ __forceinline__ void gemm_macro(Acc& acc, Pipe& pipe, const Opnd& A, 
         const double* pb1 = nullptr;
         tb1 = tb0;
         if (NBT == 2) pb1 = resolve(B, bo0 + wb + 1, kt, tb1);
-        if (pa == nullptr) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
+        if (pa == nullptr || row_pad) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
         int nmask = (pb0 != nullptr ? 1 : 0) | (pb1 != nullptr ? 2 : 0);
         if (nmask == 0) { __syncwarp(); if (lane == 0) mbar_arrive(pipe.empty + st); continue; }
         const double* sb = pipe.stages + (size_t)st * STAGE_ELEMS;
@@ -312,7 +335,11 @@ template <class F>
 __device__ __forceinline__ void acc_foreach(Acc& acc, int I, int J, F f, int rowmap = 1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, c = lane & 3;
-    const int wa = warp_row_tile(warp, rowmap), wb = warp_col_group(warp, rowmap) * NBT;
+    int wa, wb;
+    bool idle;
+    warp_tile(warp, rowmap, wa, wb, idle);
+    wb *= NBT;
+    if (idle) return;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
