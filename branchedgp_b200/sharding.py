@@ -84,3 +84,35 @@ def fit_genes_sharded(fit_one, n_genes, n_grid, group=None, device=None):
     def local(lo, hi):
         return np.stack([np.asarray(fit_one(g), dtype=np.float64).reshape(n_grid) for g in range(lo, hi)])
     return evaluate_items_sharded(local, n_genes, group=group, device=device)
+
+
+def fit_model_batch_sharded(bConsider, GPt, GPY, globalBranching, group=None, device=None, **fit_kwargs):
+    """Genome-wide sweep with the device-resident batched fit: every rank runs ``FitBranchingModel.FitModelBatch`` on its
+    contiguous block of genes (columns of ``GPY`` [N, G]) and the per-gene results that FitModel reports as scalars / small
+    vectors are gathered on every rank: ``loglik`` [G, B], ``hyperparameters`` [G, 3] (kerlen, kervar, likvar at the best
+    branching point; NaN for a failed gene) and ``Bmode`` [G].  The rank-local list of full result dictionaries (Phi,
+    prediction, posteriorB) is returned under ``local`` with its gene range ``local_range``."""
+    import torch.distributed as dist
+
+    from . import FitBranchingModel
+    G = GPY.shape[1]
+    B = len(bConsider)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(G, world, rank)
+    keep = {}
+
+    def local(lo_, hi_):
+        res = FitBranchingModel.FitModelBatch(bConsider, GPt, GPY[:, lo_:hi_], globalBranching, **fit_kwargs)
+        keep["local"] = res
+        rows = np.full((hi_ - lo_, B + 4), np.nan)
+        for k, r in enumerate(res):
+            rows[k, :B] = r["loglik"]
+            if isinstance(r["hyperparameters"], dict):
+                h = r["hyperparameters"]
+                rows[k, B:B + 3] = [float(h["kerlen"]), float(h["kervar"]), float(h["likvar"])]
+                rows[k, B + 3] = r["posteriorB"]["Bmode"]
+        return rows
+
+    full = evaluate_items_sharded(local, G, group=group, device=device)
+    return dict(loglik=full[:, :B], hyperparameters=full[:, B:B + 3], Bmode=full[:, B + 3], local=keep.get("local", []),
+                local_range=(lo, hi))

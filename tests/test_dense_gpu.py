@@ -190,3 +190,29 @@ def test_full_size_properties_without_oracle(engine):
     fd = (ep - em) / (2 * eps)
     an = float((out["grad_hyp"][0, :3] * d[0]).sum())
     assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (fd, an)
+
+
+def test_c5_shape_n2000_item_matches_oracle_and_properties(engine):
+    """BASELINE configs[4] shape: N = 2000 cells (M = 6000, 47 macro blocks, 0.7 GB workspace per item).  Two items: one against
+    the numpy oracle, and the size-independent properties (row-shift invariance, zero row sums of the softmax gradient,
+    directional finite difference along the hyper-parameters) on both."""
+    pr = make_problem(2000, D=1, n_genes=1, bs=(0.35, 0.7), seed=9)
+    args = (pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"])
+    out = engine.dense_elbo_grad(*args, pr["hyp"], pr["logPhi"])
+    assert np.all(out["status"] == 0)
+    b, h = pr["b"][0], pr["hyp"][0]
+    e, g = bgp_numpy.dense_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], _pz(pr, b), b, h[0], h[1], h[2])
+    _check_item(out, 0, e, g)
+    for k in range(2):
+        gk = out["grad_logPhi"][k]
+        assert np.abs(gk.sum(axis=1)).max() <= 1e-9 * np.abs(gk).sum(axis=1).max()
+    lp2 = pr["logPhi"] + np.random.default_rng(0).standard_normal((2, 2000, 1))
+    out2 = engine.dense_elbo_grad(*args, pr["hyp"], lp2, want_grad=False)
+    assert np.all(np.abs(out2["elbo"] - out["elbo"]) <= 1e-9 * np.abs(out["elbo"]))
+    d = np.array([[0.3, -0.2, 0.1]])
+    eps = 1e-5
+    ep = engine.dense_elbo_grad(*args, pr["hyp"] + eps * d, pr["logPhi"], want_grad=False)["elbo"]
+    em = engine.dense_elbo_grad(*args, pr["hyp"] - eps * d, pr["logPhi"], want_grad=False)["elbo"]
+    fd = (ep - em) / (2 * eps)
+    an = (out["grad_hyp"][:, :3] * d).sum(axis=1)
+    assert np.all(np.abs(fd - an) <= 1e-5 * np.maximum(1.0, np.abs(an))), (fd, an)
