@@ -20,6 +20,8 @@ import time
 
 # bgp_dense_elbo_grad_host keeps up to 16 item groups in flight on their own streams (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
