@@ -6,6 +6,9 @@
 //     (i, j, t_i <= b, prior[i]) -- pZ_construction_singleBP.py:6-25.
 // backward (SURVEY.md App. B.1 last line):
 //     Sbar = a (Abar_j + sum_d Y_id vbar_jd - w (log Phi + 1 - log pZ));  dlogPhi = S (Sbar - sum_k S_ik Sbar_ik)
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "bgp_dense.cuh"
 #include "bgp_phi.cuh"
 #include "bgp_launch.h"
@@ -36,8 +39,8 @@ __device__ __forceinline__ double log_pz(int model, bool act, bool inblock, int 
     return log(SQ_A * w + SQ_B);
 }
 
-constexpr int PHI_DCH = 4;
-
+// PHI_DCH = outputs accumulated per sweep of the column pass: 1 for single-output models (every BGP FitModel call), else 4.
+template <int PHI_DCH>
 __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     __shared__ double lse_s[PHI_RCH];
     __shared__ double Ys[PHI_RCH][PHI_DCH];
@@ -49,6 +52,18 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     const int nr = min(PHI_RCH, N - r0);
     const double* lp = P.logPhi + ((size_t)item * N + r0) * M;
     const double b = P.bv[(size_t)P.item0 * P.SD + slot];
+    // The gradient buffer of the item doubles as a stash between the passes (bound + gradient calls only): pass 1 leaves
+    // e = exp(x - max) there, pass 2 turns it into the softmax value S, and the backward kernel starts from S -- one exp per
+    // element in the whole evaluation instead of three.  With several sub-problems per item (MBGP multi-output, SD > 1) the
+    // CTAs of different sub-problems share the rows, so only S is stashed (by sub-problem 0) and pass 2 recomputes the exp.
+    double* stash = P.grad_logPhi ? P.grad_logPhi + ((size_t)item * N + r0) * M : nullptr;
+    const bool stash_e = stash != nullptr && P.SD == 1;
+    const bool stash_S = stash != nullptr && (P.SD == 1 || slot % P.SD == 0);
+    __shared__ double inv_s[PHI_RCH];
+    __shared__ int act_s[PHI_RCH];
+    if (tid < PHI_RCH) act_s[tid] = (tid < nr && P.t[r0 + tid] > b) ? 1 : 0;
+    const int model = P.model;
+    const double* prior = P.prior;
     // ---- row log-sum-exp, one warp per row (max pass, then exp-sum pass; a branchy one-pass online variant measured slower)
     for (int rr = warp; rr < nr; rr += NTHREADS / 32) {
         const double* row = lp + (size_t)rr * M;
@@ -56,11 +71,17 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
         for (int j = lane; j < M; j += 32) m = fmax(m, row[j]);
         m = warp_max(m);
         double s = 0.0;
-        for (int j = lane; j < M; j += 32) s += exp(row[j] - m);
+        if (stash_e) {
+            double* srow = stash + (size_t)rr * M;
+            for (int j = lane; j < M; j += 32) { const double e = exp(row[j] - m); srow[j] = e; s += e; }
+        } else {
+            for (int j = lane; j < M; j += 32) s += exp(row[j] - m);
+        }
         s = warp_sum(s);
         const double l = m + log(s);
         if (lane == 0) {
             lse_s[rr] = l;
+            inv_s[rr] = 1.0 / s;
             P.lse[(size_t)slot * P.slot_stride + r0 + rr] = l;
         }
     }
@@ -78,19 +99,28 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
         }
         __syncthreads();
         for (int j = tid; j < Mp; j += NTHREADS) {
-            double a = 0.0, vv[PHI_DCH] = {0.0, 0.0, 0.0, 0.0};
+            double a = 0.0, vv[PHI_DCH];
+#pragma unroll
+            for (int dd = 0; dd < PHI_DCH; ++dd) vv[dd] = 0.0;
             if (j < M) {
-                const int cell = j / 3, f = j - 3 * cell;
                 for (int rr = 0; rr < nr; ++rr) {
                     const int row = r0 + rr;
-                    const bool inblock = (cell == row);
-                    const bool act = P.t[row] > b;
-                    const double S = exp(lp[(size_t)rr * M + j] - lse_s[rr]);
-                    const double phi = phi_of(P.model, act, inblock, f, S);
+                    const int f = j - 3 * row;             // column 3*row + f belongs to the row's own cell
+                    const bool inblock = (f >= 0 && f < 3);
+                    const bool act = act_s[rr] != 0;
+                    double S;
+                    if (stash_e) {
+                        S = stash[(size_t)rr * M + j];
+                        if (d0 == 0) { S *= inv_s[rr]; stash[(size_t)rr * M + j] = S; }   // later output chunks find S itself
+                    } else {
+                        S = exp(lp[(size_t)rr * M + j] - lse_s[rr]);
+                        if (stash_S && d0 == 0) stash[(size_t)rr * M + j] = S;
+                    }
+                    const double phi = phi_of(model, act, inblock, f, S);
                     a += phi;
 #pragma unroll
                     for (int dd = 0; dd < PHI_DCH; ++dd) vv[dd] += phi * Ys[rr][dd];
-                    if (d0 == 0) kl += phi * (log(phi) - log_pz(P.model, act, inblock, f, P.prior, row, log_eps));
+                    if (d0 == 0) kl += phi * (log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps));
                 }
             }
             if (d0 == 0) P.Apart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = a;
@@ -129,9 +159,9 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_backward(PhiParams P) {
         const double l = P.lse[slot0 * P.slot_stride + row];
         double r = 0.0;
         for (int j = lane; j < M; j += 32) {
-            const int cell = j / 3, f = j - 3 * cell;
-            const bool inblock = (cell == row);
-            const double S = exp(x[j] - l);
+            const int f = j - 3 * row;
+            const bool inblock = (f >= 0 && f < 3);
+            const double S = gout[j];   // softmax value stashed by the forward pass
             const double phi = SQ_A * S + SQ_B;
             double acc = 0.0;
             for (int sd = 0; sd < SD; ++sd) {
@@ -156,76 +186,132 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_backward(PhiParams P) {
     }
 }
 
-// nsubs = sub-problems (slots) in the wave;  nitems = nsubs / SD
-// Row-resident variant of the backward pass: one CTA per row of logPhi, the row's S and Sbar live in registers
-// (EPT elements per thread), so logPhi is read once and the gradient written once, with one exp and one log per element
-// (the warp-per-row kernel above re-reads the row and recomputes the exp for its second pass).  grid (N, items).
-template <int BT, int EPT>
-__global__ void __launch_bounds__(BT) k_phi_backward_rows(PhiParams P) {
+// Row-resident backward pass: the softmax values S (stashed by the forward pass in the gradient buffer) and Sbar of one row of
+// logPhi live in registers (EPT elements per thread), so the stash is read once and the gradient written once over it, with one
+// log per element.  A row is owned by one CTA, or -- rows longer than 6144 columns (N > 2048, e.g. the N = 10 000 sparse
+// configuration) -- by a thread-block cluster of CL CTAs that exchange their partial sums of S . Sbar through distributed
+// shared memory.  grid (N * CL, items).
+// SIMPLE: one sub-problem per item and one output (every BGP FitModel call): the loops over sub-problems / outputs and their
+// pointer arithmetic disappear from the per-element code (ncu: 248 -> ~120 executed instructions per element).
+template <int BT, int EPT, int MINB, int CL, bool SIMPLE>
+__global__ void __launch_bounds__(BT, MINB) k_phi_backward_rows(PhiParams P) {
     __shared__ double red[32];
+    __shared__ double part;
     const int tid = threadIdx.x;
-    const int row = blockIdx.x, litem = blockIdx.y, item = P.item0 + litem;
+    const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+    const int row = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int litem = blockIdx.y, item = P.item0 + litem;
     const int N = P.N, M = P.M, Mp = P.Mp, D = P.D, SD = P.SD;
+    const int j0 = rank * BT * EPT;
     const double log_eps = log(1e-6);
     const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
     const double* bvi = P.bv + (size_t)item * SD;
     const size_t slot0 = (size_t)litem * SD;
-    const double* x = P.logPhi + ((size_t)item * N + row) * M;
     double* gout = P.grad_logPhi + ((size_t)item * N + row) * M;
     const double ti = P.t[row];
     int nact = 0;
     for (int sd = 0; sd < SD; ++sd) nact += (P.model == MODEL_BGP || ti > bvi[sd]) ? 1 : 0;
-    if (nact == 0) {   // uniform over the CTA
-        for (int j = tid; j < M; j += BT) gout[j] = 0.0;
+    if (nact == 0) {   // uniform over the CTAs of the row
+        for (int j = j0 + tid; j < M && j < j0 + BT * EPT; j += BT) gout[j] = 0.0;
         return;
     }
     const bool act0 = ti > bvi[0];
-    const double l = P.lse[slot0 * P.slot_stride + row];
+    // loop invariants in registers (the parameter block lives in constant memory)
+    const int model = P.model;
+    const double* prior = P.prior;
+    const double klw = P.kl_weight * (double)nact;
+    const double* Abar0 = P.Abar + slot0 * P.slot_stride;
+    const double* vbar0 = P.vbar + slot0 * P.slot_stride;
+    const double y0 = Yg[(size_t)row * P.Dtot];
     double S[EPT], sb[EPT];
     double r = 0.0;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-        const int j = tid + e * BT;
+        const int j = j0 + tid + e * BT;
         S[e] = 0.0; sb[e] = 0.0;
         if (j < M) {
-            const int cell = j / 3, f = j - 3 * cell;
-            const bool inblock = (cell == row);
-            const double s_ = exp(x[j] - l);
+            const int f = j - 3 * row;
+            const bool inblock = (f >= 0 && f < 3);
+            const double s_ = gout[j];   // softmax value stashed by the forward pass
             const double phi = SQ_A * s_ + SQ_B;
             double acc = 0.0;
-            for (int sd = 0; sd < SD; ++sd) {
-                if (!(P.model == MODEL_BGP || ti > bvi[sd])) continue;
-                const double* Abar = P.Abar + (slot0 + sd) * P.slot_stride;
-                const double* vbar = P.vbar + (slot0 + sd) * P.slot_stride;
-                const int yc = (SD > 1) ? sd : 0;
-                double yv = 0.0;
-                for (int d = 0; d < D; ++d) yv += Yg[(size_t)row * P.Dtot + yc + d] * vbar[(size_t)d * Mp + j];
-                acc += Abar[j] + yv;
+            if (SIMPLE) {
+                acc = Abar0[j] + y0 * vbar0[j];
+            } else {
+                for (int sd = 0; sd < SD; ++sd) {
+                    if (!(model == MODEL_BGP || ti > bvi[sd])) continue;
+                    const double* Abar = P.Abar + (slot0 + sd) * P.slot_stride;
+                    const double* vbar = P.vbar + (slot0 + sd) * P.slot_stride;
+                    const int yc = (SD > 1) ? sd : 0;
+                    double yv = 0.0;
+                    for (int d = 0; d < D; ++d) yv += Yg[(size_t)row * P.Dtot + yc + d] * vbar[(size_t)d * Mp + j];
+                    acc += Abar[j] + yv;
+                }
             }
-            const double lpz = log_pz(P.model, P.model == MODEL_BGP ? act0 : true, inblock, f, P.prior, row, log_eps);
-            const double v = SQ_A * (acc - P.kl_weight * (double)nact * (log(phi) + 1.0 - lpz));
+            const double lpz = log_pz(model, model == MODEL_BGP ? act0 : true, inblock, f, prior, row, log_eps);
+            const double v = SQ_A * (acc - klw * (log(phi) + 1.0 - lpz));
             S[e] = s_; sb[e] = v;
             r += s_ * v;
         }
     }
     r = block_sum(r, red);
+    if (CL > 1) {   // sum the partials of the row's CTAs in rank order (deterministic) through distributed shared memory
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        if (tid == 0) part = r;
+        cluster.sync();
+        double rt = 0.0;
+        for (int c = 0; c < CL; ++c) rt += *cluster.map_shared_rank(&part, c);
+        cluster.sync();   // nobody leaves while its partial may still be read
+        r = rt;
+    }
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-        const int j = tid + e * BT;
+        const int j = j0 + tid + e * BT;
         if (j < M) gout[j] = S[e] * (sb[e] - r);
     }
 }
 
+template <int BT, int EPT, int MINB, int CL>
+static void launch_rows_cluster(const PhiParams& P, int nitems, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P.N * CL, nitems);
+    cfg.blockDim = dim3(BT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (P.SD == 1 && P.D == 1) cudaLaunchKernelEx(&cfg, k_phi_backward_rows<BT, EPT, MINB, CL, true>, P);
+    else cudaLaunchKernelEx(&cfg, k_phi_backward_rows<BT, EPT, MINB, CL, false>, P);
+}
+
 void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
     dim3 grid(P.nch, nsubs);
-    k_phi_forward<<<grid, NTHREADS, 0, st>>>(P);
+    if (P.D == 1) k_phi_forward<1><<<grid, NTHREADS, 0, st>>>(P);
+    else k_phi_forward<4><<<grid, NTHREADS, 0, st>>>(P);
 }
 void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
     dim3 rows(P.N, nitems);
-    if (P.M <= 256 * 4) k_phi_backward_rows<256, 4><<<rows, 256, 0, st>>>(P);
-    else if (P.M <= 256 * 12) k_phi_backward_rows<256, 12><<<rows, 256, 0, st>>>(P);
-    else if (P.M <= 512 * 12) k_phi_backward_rows<512, 12><<<rows, 512, 0, st>>>(P);
-    else {   // rows too long for one CTA's registers: warp-per-row two-pass kernel
+    static const int big = getenv("BGP_PHI_BWD_BIG") ? atoi(getenv("BGP_PHI_BWD_BIG")) : 1;   // experiment switch
+    const bool simple = (P.SD == 1 && P.D == 1);
+    if (P.M <= 256 * 4) {
+        if (simple) k_phi_backward_rows<256, 4, 4, 1, true><<<rows, 256, 0, st>>>(P);
+        else k_phi_backward_rows<256, 4, 4, 1, false><<<rows, 256, 0, st>>>(P);
+    } else if (P.M <= 512 * 6) {
+        if (simple) k_phi_backward_rows<512, 6, 2, 1, true><<<rows, 512, 0, st>>>(P);
+        else k_phi_backward_rows<512, 6, 2, 1, false><<<rows, 512, 0, st>>>(P);
+    } else if (P.M <= 512 * 12) {
+        if (simple) k_phi_backward_rows<512, 12, 1, 1, true><<<rows, 512, 0, st>>>(P);
+        else k_phi_backward_rows<512, 12, 1, 1, false><<<rows, 512, 0, st>>>(P);
+    }
+    else if (P.M <= 4 * 512 * 8 && big != 2) launch_rows_cluster<512, 8, 2, 4>(P, nitems, st);
+    else if (P.M <= 8 * 512 * 8 && big == 0) launch_rows_cluster<512, 8, 1, 8>(P, nitems, st);
+    else if (P.M <= 8 * 512 * 8 && big == 1) launch_rows_cluster<512, 8, 2, 8>(P, nitems, st);
+    else if (P.M <= 8 * 1024 * 4 && big == 3) launch_rows_cluster<1024, 4, 1, 8>(P, nitems, st);
+    else {   // rows too long even for a cluster's registers: warp-per-row two-pass kernel
         dim3 grid(P.nch, nitems);
         k_phi_backward<<<grid, NTHREADS, 0, st>>>(P);
     }
