@@ -57,6 +57,7 @@ SlotLayout slot_layout(const DenseDims& d) {
     L.vpart = take((size_t)d.nch * d.D * d.Mp);
     L.klpart = take(d.nch);
     L.lse = take(d.N);
+    L.klrow = take((size_t)d.N * PHI_KLW);
     L.total = o;
     return L;
 }
@@ -90,6 +91,7 @@ int bgp_destroy(bgp_handle* h) {
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
+    if (h->fit_state) cudaFree(h->fit_state);
     delete h;
     return BGP_OK;
 }
@@ -107,6 +109,11 @@ int bgp_host_alloc(void** p, size_t bytes) { return cudaHostAlloc(p, bytes, cuda
 int bgp_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BGP_OK : BGP_ERR_CUDA; }
 
 }  // extern "C"
+// The optimiser state cached by the last fit is given back before an evaluation entry point budgets device memory.
+static void drop_fit_state(bgp_handle* h) {
+    if (h->fit_state && !h->in_fit) { cudaFree(h->fit_state); h->fit_state = nullptr; h->fit_state_bytes = 0; }
+}
+
 int ensure_ws(bgp_handle* h, size_t bytes) {
     if (h->ws_bytes >= bytes) return BGP_OK;
     if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
@@ -161,6 +168,7 @@ int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const dou
     F.logPhi = logPhi; F.t = t; F.prior = prior; F.bv = b; F.Y = Y; F.item_gene = item_gene;
     F.lse = (double*)(base + SL.lse); F.Apart = (double*)(base + SL.Apart); F.vpart = (double*)(base + SL.vpart);
     F.klpart = (double*)(base + SL.klpart);
+    F.klrow = (double*)(base + SL.klrow);
     F.slot_stride = (long long)stride_d;
     const VecLayout VL = vec_layout(d.Mp, d.nM, D);
     F.Abar = P.vec + VL.Abar; F.vbar = P.vec + VL.vbar;
@@ -226,6 +234,7 @@ int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t,
                               grad_logPhi, status);
     if (rc != BGP_OK) return rc;
     CU(cudaSetDevice(h->device));
+    drop_fit_state(h);
     const SlotLayout SL = slot_layout(make_dims(N, D));
     const int slots = pick_slots(h, count, SL.total);
     if (slots < 1) return fail(h, BGP_ERR_NOMEM, "one dense work item at N=%d needs %zu bytes of workspace", N, SL.total);
@@ -260,6 +269,7 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
                               grad_logPhi, status);
     if (rc != BGP_OK) return rc;
     CU(cudaSetDevice(h->device));
+    drop_fit_state(h);
     const size_t M = 3 * (size_t)N;
     const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
     const SlotLayout SL = slot_layout(make_dims(N, D));
@@ -383,6 +393,7 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     if (want_grad && (!grad_hyp || !grad_logPhi)) return fail(h, BGP_ERR_ARG, "want_grad needs grad_hyp and grad_logPhi");
     if (kernel_kind != BGP_KERNEL_MATERN32 && kernel_kind != BGP_KERNEL_SQEXP) return fail(h, BGP_ERR_ARG, "unknown kernel kind %d", kernel_kind);
     CU(cudaSetDevice(h->device));
+    drop_fit_state(h);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int SD = multi ? Dtot : 1, D = multi ? 1 : Dtot;
     const int M = 3 * N, Mp = (M + SP_SL - 1) / SP_SL * SP_SL;
@@ -422,7 +433,7 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     F.N = N; F.M = M; F.Mp = Mp; F.D = D; F.nch = nch; F.model = model; F.kl_weight = 1.0; F.SD = SD; F.Dtot = Dtot;
     F.slot_stride = SL.total;
     F.logPhi = logPhi; F.t = t; F.prior = prior; F.bv = b; F.Y = Y; F.item_gene = item_gene;
-    F.lse = wsd + SL.lse; F.Apart = wsd + SL.Apart; F.vpart = wsd + SL.vpart; F.klpart = wsd + SL.klpart;
+    F.lse = wsd + SL.lse; F.Apart = wsd + SL.Apart; F.vpart = wsd + SL.vpart; F.klpart = wsd + SL.klpart; F.klrow = wsd + SL.klrow;
     F.Abar = wsd + SL.Abar; F.vbar = wsd + SL.vbar; F.grad_logPhi = grad_logPhi;
 
     for (int item0 = 0; item0 < count; item0 += items_cap) {

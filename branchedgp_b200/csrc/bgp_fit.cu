@@ -857,12 +857,14 @@ static int fit_common(bgp_handle* h, bool sparse, int count, int N, int D, int M
     if (h->stage) { cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const size_t avail = (size_t)(0.92 * (double)(free_b + h->ws_bytes));
+    const size_t avail = (size_t)(0.92 * (double)(free_b + h->ws_bytes + h->fit_state_bytes));
     const size_t fixed = (size_t)nY * N * D * 8 + ((size_t)64 << 20);
     if (avail < fixed + state_per_slot + eval_per_slot) return fail(h, BGP_ERR_NOMEM, "one work item at N=%d does not fit in device memory", N);
     const size_t fit = (avail - fixed) / (state_per_slot + eval_per_slot);
     if ((size_t)S > fit) S = (int)fit;
     if (!sparse) {
+        // the workspace is grow-only; a larger one left by a host-pointer call would not be covered by the budget above
+        if (h->ws && h->ws_bytes > (size_t)S * SL.total) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
         rc = ensure_ws(h, (size_t)S * SL.total);
         if (rc != BGP_OK) return rc;
     }
@@ -881,8 +883,14 @@ static int fit_common(bgp_handle* h, bool sparse, int count, int N, int D, int M
         probe.take<double>((size_t)S * Tq); probe.take<double>((size_t)3 * (Mz + 1) * Tq);
         need = probe.off + 4096;
     }
-    cudaError_t ce = cudaMalloc((void**)&B.base, need);
-    if (ce != cudaSuccess) { cudaGetLastError(); return fail(h, BGP_ERR_NOMEM, "optimiser state of %zu bytes: %s", need, cudaGetErrorString(ce)); }
+    // the optimiser state is kept in the handle between calls (FitModelBatch calls once per grid point); grow-only
+    if (h->fit_state_bytes < need) {
+        if (h->fit_state) { cudaFree(h->fit_state); h->fit_state = nullptr; h->fit_state_bytes = 0; }
+        cudaError_t ce = cudaMalloc(&h->fit_state, need);
+        if (ce != cudaSuccess) { cudaGetLastError(); return fail(h, BGP_ERR_NOMEM, "optimiser state of %zu bytes: %s", need, cudaGetErrorString(ce)); }
+        h->fit_state_bytes = need;
+    }
+    B.base = (char*)h->fit_state;
     B.cap = need;
     FitVecs V;
     V.n = n; V.m = m;
@@ -906,13 +914,12 @@ static int fit_common(bgp_handle* h, bool sparse, int count, int N, int D, int M
     double* d_mean = B.take<double>((size_t)S * Tq * D);
     double* d_var = B.take<double>((size_t)S * Tq);
     double* d_scr = B.take<double>((size_t)3 * (Mz + 1) * Tq);
-    auto bail = [&](int code) { cudaFree(B.base); return code; };
+    auto bail = [&](int code) { return code; };
 #define CUF(call)                                                                                                   \
     do {                                                                                                            \
         cudaError_t e_ = (call);                                                                                    \
         if (e_ != cudaSuccess) return bail(fail(h, BGP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)));         \
     } while (0)
-    CUF(cudaMemsetAsync(vecs, 0, ((size_t)S * n * (5 + 2 * m) + 64) * 8, st));
     CUF(cudaMemcpyAsync(d_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, st));
     CUF(cudaMemcpyAsync(d_Y, Y, (size_t)nY * N * D * 8, cudaMemcpyHostToDevice, st));
     CUF(cudaMemcpyAsync(d_prior, prior, (size_t)N * 16, cudaMemcpyHostToDevice, st));
@@ -985,11 +992,12 @@ static int fit_common(bgp_handle* h, bool sparse, int count, int N, int D, int M
         CU(cudaStreamSynchronize(st));   // host vectors above go out of scope; the slots are refilled next
         return BGP_OK;
     };
+    h->in_fit = true;
     rc = fit_core(F, *ev, S, V, st, d_hyp, d_b, d_gene, d_elbo, d_gh, d_status, 1, init_x, finish_slots);
+    h->in_fit = false;
     cudaFree(d_map);
     h->max_slots = saved_slots;
     cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(B.base);
     if (rc == BGP_OK && e2 != cudaSuccess) rc = fail(h, BGP_ERR_CUDA, "fit: %s", cudaGetErrorString(e2));
     return rc;
 #undef CUF

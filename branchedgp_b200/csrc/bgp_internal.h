@@ -21,6 +21,10 @@ struct bgp_handle {
     // staging for the _host entry points (grow-only)
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    // optimiser state of the batched fit (bgp_fit.cu), kept between calls (grow-only)
+    void* fit_state = nullptr;
+    size_t fit_state_bytes = 0;
+    bool in_fit = false;       // set while a fit call runs: its evaluator calls must not drop the state to make room
     // description of the last dense wave, for the debug readers
     bgp::DenseParams lastP;
     bgp::SparseParams lastS;        // parameters of the last sparse wave (device pointers into the staging area stay valid
@@ -55,7 +59,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 bgp::DenseDims make_dims(int N, int D);
 
 struct SlotLayout {   // byte offsets inside one slot
-    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, total;
+    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, klrow, total;
 };
 SlotLayout slot_layout(const bgp::DenseDims& d);
 int ensure_ws(bgp_handle* h, size_t bytes);

@@ -7,7 +7,6 @@
 // backward (SURVEY.md App. B.1 last line):
 //     Sbar = a (Abar_j + sum_d Y_id vbar_jd - w (log Phi + 1 - log pZ));  dlogPhi = S (Sbar - sum_k S_ik Sbar_ik)
 #include <cooperative_groups.h>
-#include <cstdlib>
 
 #include "bgp_dense.cuh"
 #include "bgp_phi.cuh"
@@ -129,6 +128,131 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     }
     kl = block_sum(kl, red);
     if (tid == 0) P.klpart[(size_t)slot * P.slot_stride + chunk] = kl;
+}
+
+// ---------------------------------------------------------------------------------------------------- row-resident forward
+// Bound + gradient calls with one sub-problem per item: the forward pass is split into a row pass and a column pass.
+//   k_phi_rowpass: one CTA (or a cluster of CL CTAs) owns one row of logPhi, which it reads ONCE into registers: max, e = exp(x - max),
+//                  sum, S = e / sum (written to the stash in the gradient buffer), Phi, the row's KL terms.  One exp and one log per
+//                  element; a cluster combines its CTAs' (max, sum) pairs through distributed shared memory.
+//   k_phi_colpass: thread per column over 16-row chunks of the stash: A = sum_i Phi, v = Phi^T Y (no transcendentals).
+// DRAM traffic per element: 8 B read + 8 B written + 8 B read, against 40 B for k_phi_forward at rows longer than the L2 can hold.
+template <int BT, int EPT, int MINB, int CL>
+__global__ void __launch_bounds__(BT, MINB) k_phi_rowpass(PhiParams P) {
+    __shared__ double red[32];
+    __shared__ double xch[2];
+    const int tid = threadIdx.x;
+    const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+    const int row = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int slot = blockIdx.y, item = P.item0 + slot;
+    const int N = P.N, M = P.M;
+    const int j0 = rank * BT * EPT;
+    const int model = P.model;
+    const double* prior = P.prior;
+    const double* x = P.logPhi + ((size_t)item * N + row) * M;
+    double* stash = P.grad_logPhi + ((size_t)item * N + row) * M;
+    const bool act = P.t[row] > P.bv[item];
+    const double log_eps = log(1e-6);
+    double e[EPT];
+    double m = -1.0e308;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int j = j0 + tid + k * BT;
+        e[k] = (j < M) ? x[j] : -1.0e308;
+        m = fmax(m, e[k]);
+    }
+    // block maximum
+    m = warp_max(m);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    m = (tid & 31) < BT / 32 ? red[tid & 31] : -1.0e308;
+    m = warp_max(m);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int j = j0 + tid + k * BT;
+        e[k] = (j < M) ? exp(e[k] - m) : 0.0;
+        s += e[k];
+    }
+    s = block_sum(s, red);
+    double scale = 1.0 / s, lse = m + log(s);
+    if (CL > 1) {   // combine the (max, sum) pairs of the row's CTAs in rank order
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        if (tid == 0) { xch[0] = m; xch[1] = s; }
+        cluster.sync();
+        double mg = -1.0e308;
+        for (int c = 0; c < CL; ++c) mg = fmax(mg, cluster.map_shared_rank(xch, c)[0]);
+        double sg = 0.0;
+        for (int c = 0; c < CL; ++c) { const double* o = cluster.map_shared_rank(xch, c); sg += o[1] * exp(o[0] - mg); }
+        cluster.sync();   // nobody leaves (or reuses xch) while it may still be read
+        scale = exp(m - mg) / sg;
+        lse = mg + log(sg);
+    }
+    if (tid == 0 && rank == 0) P.lse[(size_t)slot * P.slot_stride + row] = lse;
+    double kl = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int j = j0 + tid + k * BT;
+        if (j < M) {
+            const double S = e[k] * scale;
+            stash[j] = S;
+            const int f = j - 3 * row;
+            const bool inblock = (f >= 0 && f < 3);
+            const double phi = phi_of(model, act, inblock, f, S);
+            kl += phi * (log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps));
+        }
+    }
+    kl = block_sum(kl, red);
+    if (tid == 0) P.klrow[(size_t)slot * P.slot_stride + (size_t)row * PHI_KLW + rank] = kl;
+}
+
+template <int PHI_DCH>
+__global__ void __launch_bounds__(NTHREADS) k_phi_colpass(PhiParams P, int ncl) {
+    __shared__ double Ys[PHI_RCH][PHI_DCH];
+    __shared__ int act_s[PHI_RCH];
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.x, slot = blockIdx.y, item = P.item0 + slot;
+    const int N = P.N, M = P.M, Mp = P.Mp, D = P.D;
+    const int r0 = chunk * PHI_RCH;
+    const int nr = min(PHI_RCH, N - r0);
+    const int model = P.model;
+    const double b = P.bv[item];
+    const double* stash = P.grad_logPhi + ((size_t)item * N + r0) * M;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    if (tid < PHI_RCH) act_s[tid] = (tid < nr && P.t[r0 + tid] > b) ? 1 : 0;
+    if (tid == 0) {   // KL of the chunk: the rows' partials in a fixed order
+        double kl = 0.0;
+        for (int rr = 0; rr < nr; ++rr)
+            for (int c = 0; c < ncl; ++c) kl += P.klrow[(size_t)slot * P.slot_stride + (size_t)(r0 + rr) * PHI_KLW + c];
+        P.klpart[(size_t)slot * P.slot_stride + chunk] = kl;
+    }
+    for (int d0 = 0; d0 < D; d0 += PHI_DCH) {
+        const int nd = min(PHI_DCH, D - d0);
+        __syncthreads();
+        if (tid < PHI_RCH * PHI_DCH) {
+            const int rr = tid / PHI_DCH, dd = tid % PHI_DCH;
+            Ys[rr][dd] = (rr < nr && dd < nd) ? Yg[(size_t)(r0 + rr) * P.Dtot + d0 + dd] : 0.0;
+        }
+        __syncthreads();
+        for (int j = tid; j < Mp; j += NTHREADS) {
+            double a = 0.0, vv[PHI_DCH];
+#pragma unroll
+            for (int dd = 0; dd < PHI_DCH; ++dd) vv[dd] = 0.0;
+            if (j < M) {
+                for (int rr = 0; rr < nr; ++rr) {
+                    const int f = j - 3 * (r0 + rr);
+                    const double phi = phi_of(model, act_s[rr] != 0, f >= 0 && f < 3, f, stash[(size_t)rr * M + j]);
+                    a += phi;
+#pragma unroll
+                    for (int dd = 0; dd < PHI_DCH; ++dd) vv[dd] += phi * Ys[rr][dd];
+                }
+            }
+            if (d0 == 0) P.Apart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = a;
+            for (int dd = 0; dd < nd; ++dd) P.vpart[(size_t)slot * P.slot_stride + ((size_t)chunk * D + d0 + dd) * Mp + j] = vv[dd];
+        }
+    }
 }
 
 // grid (row chunks, ITEMS of the wave): sums the contributions of the item's SD sub-problems.
@@ -290,12 +414,22 @@ static void launch_rows_cluster(const PhiParams& P, int nitems, cudaStream_t st)
 
 void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
     dim3 grid(P.nch, nsubs);
+    // Row pass + column pass through the stash for rows that fit one CTA's registers.  The cluster variants of the row pass
+    // (k_phi_rowpass<512, 8, 2, 4 or 8> under a cluster launch) work but were slower than k_phi_forward at N = 10 000 (39 ms against 30 ms for 8 items:
+    // two block reductions and a cluster exchange per 4096 elements), so long rows stay with k_phi_forward.
+    if (P.grad_logPhi != nullptr && P.SD == 1 && P.M <= 512 * 12) {
+        if (P.M <= 256 * 4) k_phi_rowpass<256, 4, 4, 1><<<dim3(P.N, nsubs), 256, 0, st>>>(P);
+        else if (P.M <= 512 * 6) k_phi_rowpass<512, 6, 2, 1><<<dim3(P.N, nsubs), 512, 0, st>>>(P);
+        else k_phi_rowpass<512, 12, 1, 1><<<dim3(P.N, nsubs), 512, 0, st>>>(P);
+        if (P.D == 1) k_phi_colpass<1><<<grid, NTHREADS, 0, st>>>(P, 1);
+        else k_phi_colpass<4><<<grid, NTHREADS, 0, st>>>(P, 1);
+        return;
+    }
     if (P.D == 1) k_phi_forward<1><<<grid, NTHREADS, 0, st>>>(P);
     else k_phi_forward<4><<<grid, NTHREADS, 0, st>>>(P);
 }
 void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
     dim3 rows(P.N, nitems);
-    static const int big = getenv("BGP_PHI_BWD_BIG") ? atoi(getenv("BGP_PHI_BWD_BIG")) : 1;   // experiment switch
     const bool simple = (P.SD == 1 && P.D == 1);
     if (P.M <= 256 * 4) {
         if (simple) k_phi_backward_rows<256, 4, 4, 1, true><<<rows, 256, 0, st>>>(P);
@@ -307,10 +441,10 @@ void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
         if (simple) k_phi_backward_rows<512, 12, 1, 1, true><<<rows, 512, 0, st>>>(P);
         else k_phi_backward_rows<512, 12, 1, 1, false><<<rows, 512, 0, st>>>(P);
     }
-    else if (P.M <= 4 * 512 * 8 && big != 2) launch_rows_cluster<512, 8, 2, 4>(P, nitems, st);
-    else if (P.M <= 8 * 512 * 8 && big == 0) launch_rows_cluster<512, 8, 1, 8>(P, nitems, st);
-    else if (P.M <= 8 * 512 * 8 && big == 1) launch_rows_cluster<512, 8, 2, 8>(P, nitems, st);
-    else if (P.M <= 8 * 1024 * 4 && big == 3) launch_rows_cluster<1024, 4, 1, 8>(P, nitems, st);
+    // clusters of 4 / 8 CTAs per row; 64 registers so that two CTAs share an SM (measured at N = 10 000, 8 items: 34 ms against
+    // 73 ms with one 124-register CTA per SM, 46 ms with 1024 x 4, 50 ms for the two-pass kernel below)
+    else if (P.M <= 4 * 512 * 8) launch_rows_cluster<512, 8, 2, 4>(P, nitems, st);
+    else if (P.M <= 8 * 512 * 8) launch_rows_cluster<512, 8, 2, 8>(P, nitems, st);
     else {   // rows too long even for a cluster's registers: warp-per-row two-pass kernel
         dim3 grid(P.nch, nitems);
         k_phi_backward<<<grid, NTHREADS, 0, st>>>(P);

@@ -5,6 +5,7 @@
 namespace bgp {
 
 constexpr int PHI_RCH = 16;   // rows of logPhi handled by one CTA of the forward pass
+constexpr int PHI_KLW = 8;    // KL partials kept per row by the row-resident forward pass (one per CTA of the row's cluster)
 
 // A "sub-problem" is one (work item, output group): dense / sparse BGP have one per item carrying all D outputs
 // (SD = 1, D = Dtot); the MBGP multi-output bound has one per output (SD = Dtot, D = 1) because the trunk mask
@@ -27,6 +28,7 @@ struct PhiParams {
     double* Apart;             // [slot][nch][Mp]
     double* vpart;             // [slot][nch][D][Mp]
     double* klpart;            // [slot][nch]
+    double* klrow;             // [slot][N][PHI_KLW]  scratch of the row-resident forward pass
     // backward inputs (per slot) and output
     const double* Abar;        // [Mp]
     const double* vbar;        // [D][Mp]

@@ -60,7 +60,9 @@ def test_bound_only_equals_bound_with_gradient(engine):
     pr = make_problem(40, D=1, n_genes=1, bs=(0.3, 0.5, 1.1), seed=3)
     a = engine.dense_elbo_grad(pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"], want_grad=False)
     b = engine.dense_elbo_grad(pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"], want_grad=True)
-    assert np.array_equal(a["elbo"], b["elbo"])
+    # the bound-only call runs the one-kernel assignment pass, the gradient call the row-resident one (different summation
+    # order of the same terms): equal to rounding, not bit for bit
+    np.testing.assert_allclose(a["elbo"], b["elbo"], rtol=1e-13)
     assert a["grad_logPhi"] is None
 
 
