@@ -125,3 +125,17 @@ def test_golden_fixture_is_reproduced_by_the_numpy_oracle():
         assert np.allclose([g["ell"], g["var"], g["likvar"]], GOLD[name + "/grad_hyp"][k], rtol=1e-7, atol=1e-9)
         N = pr["N"]
         assert relerr(g["logPhi"][np.arange(N), 3 * np.arange(N) + 1], GOLD[name + "/grad_logphi_probe"][k]) <= 1e-8
+
+
+def test_oracle_fitmodel_reproduces_the_c1_golden_fixture():
+    """tests/golden/c1_fitmodel.npz is what oracle.fit_ref produces (two of the ten independent fixed-hyper-parameter fits are
+    re-run here; the full fixture takes minutes on CPU)."""
+    import os
+    sys_path_golden = os.path.join(os.path.dirname(__file__), "golden")
+    gold = np.load(os.path.join(sys_path_golden, "c1_fitmodel.npz"))
+    from golden.make_golden_c1 import MAXITER, c1_problem
+    from oracle import fit_ref
+    t, Y, labels, grid = c1_problem()
+    sub = [grid[4], grid[9]]
+    r = fit_ref.fit_model(sub, t, Y, labels, M=0, maxiter=MAXITER, fixHyperparameters=True)
+    np.testing.assert_allclose(r["loglik"], gold["fixed/loglik"][[4, 9]], rtol=1e-9)
