@@ -142,6 +142,22 @@ def init_logphi_device(torch, dev, N, phi0, t, b_items, seed):
     return lp
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: keep this rank's host threads (and with first-touch its pinned buffers) on the CPUs next to its GPU, so
+    that the host<->device copies of the e2e leg do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as ex:   # affinity is an optimisation only
+        print(f"[bench] no NUMA binding for GPU {gpu_index}: {ex}", file=sys.stderr)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -153,6 +169,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=dev)
     N, ips = args.cells, args.items
     eng = _lib.Engine(local)
@@ -314,7 +331,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:   # reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(N, H, kind="port", budget_s=args.cpu_seconds)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -405,10 +422,26 @@ def run_reference(args):
             "config": {"workload": workload_name(N), "items_per_step": per_step},
             "cpu_baseline": cb, "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    # NCCL prints its version banner on fd 1 when NCCL_DEBUG is set in the environment: send fd 1 to stderr for the whole run
+    # and keep a private handle on the original stdout for the result line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
