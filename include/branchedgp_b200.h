@@ -71,6 +71,8 @@ int bgp_host_free(void* p);
  *   elbo[count]          the bound (without hyper-priors)
  *   grad_hyp[count][4]   d elbo / d (lengthscale, kernel variance, likelihood variance, b)   (may be NULL if !want_grad)
  *   grad_logPhi[count][N][3N]                                                                 (may be NULL if !want_grad)
+ *                        -- doubles as scratch during the call (the forward assignment pass parks the softmax values there
+ *                        for the backward pass), so it must not alias logPhi
  *   status[count]
  */
 int bgp_dense_elbo_grad(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
