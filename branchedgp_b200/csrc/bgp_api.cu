@@ -256,8 +256,8 @@ int ensure_stage(bgp_handle* h, size_t bytes) {
 }
 extern "C" {
 
-// Host-pointer entry.  The items are cut into groups of about an eighth of the SMs; each group owns a lane (CUDA stream +
-// workspace slots + staging buffers) on which its H2D copy, kernels and D2H copy are queued in order.  Up to eight groups
+// Host-pointer entry.  The items are cut into groups of a quarter of the SMs; each group owns a lane (CUDA stream +
+// workspace slots + staging buffers) on which its H2D copy, kernels and D2H copy are queued in order.  Up to four groups
 // compute concurrently (their one-CTA-per-item kernels share the SMs) while the copy engines move the next / previous
 // groups, so for calls with more than one SM-count of items the PCIe time hides behind the arithmetic.
 int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, int nY,
@@ -274,11 +274,11 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
     const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
     const SlotLayout SL = slot_layout(make_dims(N, D));
     const size_t per_item = (size_t)N * M * 8;
-    int conc = 8;   // measured on B200 (tools/e2e_sweep.sh, 296 items at N = 1000): 4 groups / 8 lanes 278 items/s, 8 / 16 296, 16 / 20 262
+    int conc = 4;   // measured on B200 with 32 hardware work queues (tools/e2e_sweep.sh, 296 items at N = 1000): 2-6 groups 311-315 items/s, 8 groups 293-306, 10 groups 295
     int sm_cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
     if (sm_cap > count) sm_cap = count;
     if (const char* e = getenv("BGP_HOST_CONC")) conc = atoi(e) > 0 ? atoi(e) : conc;
-    int gs = (sm_cap + conc - 1) / conc;                 // items per group
+    int gs = sm_cap / conc;                              // items per group: conc groups never ask for more CTAs than there are SMs
     if (gs < 1) gs = 1;
     int ngroups = (count + gs - 1) / gs;
     int lanes = ngroups < 2 * conc ? ngroups : 2 * conc;
