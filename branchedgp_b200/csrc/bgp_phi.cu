@@ -1,4 +1,5 @@
-// Assignment passes over the N x 3N variational matrix logPhi (HBM-bound, fp64 transcendentals).
+// Assignment passes over the N x 3N variational matrix logPhi (HBM traffic + fp64 transcendentals: the per-element exp / log are
+// the tailored routines of bgp_math.cuh).
 //
 // forward  (assigngp_dense.py:160-162, 242-245; MBGP/assigngp.py:217-251, 688-691):
 //     S = softmax_rows(logPhi);  Phi = (1-2e-6) S + 1e-6;  A_j = sum_i Phi_ij;  v_jd = sum_i Phi_ij Y_id;
@@ -9,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "bgp_dense.cuh"
+#include "bgp_math.cuh"
 #include "bgp_phi.cuh"
 #include "bgp_launch.h"
 
@@ -72,9 +74,9 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
         double s = 0.0;
         if (stash_e) {
             double* srow = stash + (size_t)rr * M;
-            for (int j = lane; j < M; j += 32) { const double e = exp(row[j] - m); srow[j] = e; s += e; }
+            for (int j = lane; j < M; j += 32) { const double e = fast_exp(row[j] - m); srow[j] = e; s += e; }
         } else {
-            for (int j = lane; j < M; j += 32) s += exp(row[j] - m);
+            for (int j = lane; j < M; j += 32) s += fast_exp(row[j] - m);
         }
         s = warp_sum(s);
         const double l = m + log(s);
@@ -112,14 +114,14 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
                         S = stash[(size_t)rr * M + j];
                         if (d0 == 0) { S *= inv_s[rr]; stash[(size_t)rr * M + j] = S; }   // later output chunks find S itself
                     } else {
-                        S = exp(lp[(size_t)rr * M + j] - lse_s[rr]);
+                        S = fast_exp(lp[(size_t)rr * M + j] - lse_s[rr]);
                         if (stash_S && d0 == 0) stash[(size_t)rr * M + j] = S;
                     }
                     const double phi = phi_of(model, act, inblock, f, S);
                     a += phi;
 #pragma unroll
                     for (int dd = 0; dd < PHI_DCH; ++dd) vv[dd] += phi * Ys[rr][dd];
-                    if (d0 == 0) kl += phi * (log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps));
+                    if (d0 == 0) kl += phi * (fast_log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps));
                 }
             }
             if (d0 == 0) P.Apart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = a;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(BT, MINB) k_phi_rowpass(PhiParams P) {
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
         const int j = j0 + tid + k * BT;
-        e[k] = (j < M) ? exp(e[k] - m) : 0.0;
+        e[k] = (j < M) ? fast_exp(e[k] - m) : 0.0;
         s += e[k];
     }
     s = block_sum(s, red);
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(BT, MINB) k_phi_rowpass(PhiParams P) {
             const int f = j - 3 * row;
             const bool inblock = (f >= 0 && f < 3);
             const double phi = phi_of(model, act, inblock, f, S);
-            kl += phi * (log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps));
+            kl += phi * (fast_log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps));
         }
     }
     kl = block_sum(kl, red);
@@ -298,13 +300,13 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_backward(PhiParams P) {
                 acc += Abar[j] + yv;
             }
             const double lpz = log_pz(P.model, P.model == MODEL_BGP ? act0 : true, inblock, f, P.prior, row, log_eps);
-            const double sb = SQ_A * (acc - P.kl_weight * (double)nact * (log(phi) + 1.0 - lpz));
+            const double sb = SQ_A * (acc - P.kl_weight * (double)nact * (fast_log(phi) + 1.0 - lpz));
             gout[j] = sb;
             r += S * sb;
         }
         r = warp_sum(r);
         for (int j = lane; j < M; j += 32) {
-            const double S = exp(x[j] - l);
+            const double S = fast_exp(x[j] - l);
             gout[j] = S * (gout[j] - r);
         }
     }
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(BT, MINB) k_phi_backward_rows(PhiParams P) {
                 }
             }
             const double lpz = log_pz(model, model == MODEL_BGP ? act0 : true, inblock, f, prior, row, log_eps);
-            const double v = SQ_A * (acc - klw * (log(phi) + 1.0 - lpz));
+            const double v = SQ_A * (acc - klw * (fast_log(phi) + 1.0 - lpz));
             S[e] = s_; sb[e] = v;
             r += s_ * v;
         }
