@@ -88,7 +88,7 @@ def FitModel(bConsider, GPt, GPy, globalBranching, priorConfidence=0.80, M=10, l
 
 
 def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=10, likvar=1.0, kerlen=2.0, kervar=5.0,
-                  fDebug=False, maxiter=100, fPredict=True, fixHyperparameters=False, engine=None, max_slots=0):
+                  fDebug=False, maxiter=100, fPredict=True, fixHyperparameters=False, engine=None, max_slots=0, maxcor=10):
     """``FitModel`` for every gene (column of ``GPY`` [N, G]) at once: returns a list of G dictionaries with FitModel's keys.
 
     Per gene the semantics are FitModel's (FitBranchingModel.py:11-178): the same initial conditions and label prior for
@@ -97,7 +97,11 @@ def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=
     factorisation fails.  What changes is where the optimiser runs: all genes are fitted together by the device-resident
     batched L-BFGS of ``libbgp_b200`` (bgp_dense_fit_host for M = 0, bgp_sparse_fit_host otherwise) -- one call per grid
     point with G work items when the hyper-parameters are trainable (the warm start makes the grid a serial chain per
-    gene), one call with G x len(bConsider) items when ``fixHyperparameters``."""
+    gene), one call with G x len(bConsider) items when ``fixHyperparameters``.
+
+    ``maxcor`` is SciPy's number of stored L-BFGS pairs (10).  The optimiser state of an item is (5 + 2 maxcor) vectors of
+    3 N^2 doubles (0.6 GB at N = 1000, 2.4 GB at N = 2000), which bounds the number of items fitted concurrently (148 at
+    N = 1000, 52 at N = 2000 on a 180 GB B200); a smaller ``maxcor`` trades optimiser memory for more items in flight."""
     from . import _lib
     assert isinstance(bConsider, list), "Candidate B must be list"
     GPt = np.asarray(GPt, dtype=np.float64)
@@ -116,7 +120,7 @@ def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=
         Z = np.ones((M, 2))
         Z[:, 0] = np.linspace(0, 1, M, endpoint=False)
         Z[:, 1] = np.array([i for j in range(M) for i in range(1, 4)])[:M]
-    opts = eng.fit_options(maxiter=int(maxiter), train_hyp=0 if fixHyperparameters else 1, max_slots=int(max_slots))
+    opts = eng.fit_options(maxiter=int(maxiter), train_hyp=0 if fixHyperparameters else 1, max_slots=int(max_slots), maxcor=int(maxcor))
     Y = np.ascontiguousarray(GPY.T[:, :, None])          # [G, N, 1]
     lo, hi = float(np.min(GPt)), float(np.max(GPt))
 
