@@ -10,10 +10,22 @@ from .gpflow_shim import distributions as _tfd
 
 
 def FitModel(bConsider, GPt, GPy, globalBranching, priorConfidence=0.80, M=10, likvar=1.0, kerlen=2.0, kervar=5.0,
-             fDebug=False, maxiter=100, fPredict=True, fixHyperparameters=False):
+             fDebug=False, maxiter=100, fPredict=True, fixHyperparameters=False, *, optimizer="scipy"):
     """Fit the BGP model for every candidate branching point in ``bConsider`` (warm-starting the hyper-parameters from
     one grid point to the next, as the reference does) and return
-    ``{loglik, Phi, prediction{xtest, mu, var}, hyperparameters, posteriorB}``."""
+    ``{loglik, Phi, prediction{xtest, mu, var}, hyperparameters, posteriorB}``.
+
+    ``optimizer="scipy"`` (default) is the reference's own driver: SciPy L-BFGS-B calling the CUDA bound once per function
+    evaluation.  ``optimizer="device"`` (keyword only, not in the reference) hands the same problem to the device-resident
+    batched L-BFGS of ``FitModelBatch`` -- with ``fixHyperparameters`` all grid points are then fitted concurrently."""
+    if optimizer == "device":
+        assert GPy.ndim == 2 and GPy.shape[1] == 1, "the BGP model fits one gene (FitBranchingModel.py:47-49)"
+        res = FitModelBatch(bConsider, GPt, GPy, globalBranching, priorConfidence=priorConfidence, M=M, likvar=likvar, kerlen=kerlen,
+                            kervar=kervar, fDebug=fDebug, maxiter=maxiter, fPredict=fPredict, fixHyperparameters=fixHyperparameters)[0]
+        res.pop("fit", None)
+        return res
+    if optimizer != "scipy":
+        raise ValueError("optimizer must be 'scipy' or 'device'")
     assert isinstance(bConsider, list), "Candidate B must be list"
     assert GPt.ndim == 1
     assert GPy.ndim == 2

@@ -133,6 +133,40 @@ __device__ __forceinline__ double kuf_entry(const SparseParams& P, const double*
     return (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
 }
 
+constexpr int SP_RB = 4;   // rows per warp pass in the slab products
+
+// dst[m][n] (+)= sign * sum_jj A[m][jj] B[n][jj] for n <= m, A / B = [Mz][SP_SL + 1] slabs in shared memory.  Four rows m per warp
+// pass: every B row fetched from shared memory feeds four accumulators.
+__device__ __forceinline__ void slab_outer_lower(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ dst,
+                                                 int Mz, bool first, double sign, int warp, int lane) {
+    const int LDS_ = SP_SL + 1;
+    for (int m0 = SP_RB * warp; m0 < Mz; m0 += SP_RB * (NTHREADS / 32)) {
+        const int mtop = min(m0 + SP_RB - 1, Mz - 1);
+        const double* ar[SP_RB];
+#pragma unroll
+        for (int r = 0; r < SP_RB; ++r) ar[r] = A + (size_t)min(m0 + r, Mz - 1) * LDS_;
+        for (int n = lane; n <= mtop; n += 32) {
+            double sacc[SP_RB];
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r) sacc[r] = 0.0;
+            const double* bn = B + (size_t)n * LDS_;
+#pragma unroll 8
+            for (int jj = 0; jj < SP_SL; ++jj) {
+                const double x = bn[jj];
+#pragma unroll
+                for (int r = 0; r < SP_RB; ++r) sacc[r] += ar[r][jj] * x;
+            }
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r) {
+                const int m = m0 + r;
+                if (m >= Mz || n > m) continue;
+                double* d = dst + (size_t)m * Mz + n;
+                *d = first ? sign * sacc[r] : (*d + sign * sacc[r]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- k_sp_kuu
 __global__ void __launch_bounds__(NTHREADS) k_sp_kuu(SparseParams P) {
     SP_SETUP();
@@ -190,13 +224,27 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
         __syncthreads();
-        for (int m = warp; m < Mz; m += NTHREADS / 32) {
-            const double* lr = Linv + (size_t)m * Mz;
-            double s = 0.0;
-            for (int k = 0; k <= m; ++k) s += lr[k] * Ks[k * LDS_ + lane];
-            Vs[m * LDS_ + lane] = s;
-            if (!empty && j0 + lane < Mp) ws[SLy.V + (size_t)m * Mp + j0 + lane] = s;
-            tr += Dls[lane] * s * s;
+        // four rows per warp pass: four independent accumulators share every shared-memory load of Ks (Linv is stored as a
+        // full square with explicit zeros above the diagonal, so the four rows run over the same k range)
+        for (int m0 = SP_RB * warp; m0 < Mz; m0 += SP_RB * (NTHREADS / 32)) {
+            const double* lr[SP_RB];
+            double sacc[SP_RB];
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r) { lr[r] = Linv + (size_t)min(m0 + r, Mz - 1) * Mz; sacc[r] = 0.0; }
+            const int kend = min(m0 + SP_RB - 1, Mz - 1);
+            for (int k = 0; k <= kend; ++k) {
+                const double x = Ks[k * LDS_ + lane];
+#pragma unroll
+                for (int r = 0; r < SP_RB; ++r) sacc[r] += lr[r][k] * x;
+            }
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r) {
+                const int m = m0 + r;
+                if (m >= Mz) break;
+                Vs[m * LDS_ + lane] = sacc[r];
+                if (!empty && j0 + lane < Mp) ws[SLy.V + (size_t)m * Mp + j0 + lane] = sacc[r];
+                tr += Dls[lane] * sacc[r] * sacc[r];
+            }
         }
         __syncthreads();
         // Ks <- Delta_j V (scaled copy) so that P += Ks Vs^T
@@ -205,14 +253,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
             Ks[m * LDS_ + jj] = Dls[jj] * Vs[m * LDS_ + jj];
         }
         __syncthreads();
-        for (int m = warp; m < Mz; m += NTHREADS / 32)
-            for (int n = lane; n <= m; n += 32) {
-                double s = 0.0;
-#pragma unroll 8
-                for (int jj = 0; jj < SP_SL; ++jj) s += Ks[m * LDS_ + jj] * Vs[n * LDS_ + jj];
-                double* dst = Pp + (size_t)m * Mz + n;
-                *dst = first ? s : (*dst + s);
-            }
+        slab_outer_lower(Ks, Vs, Pp, Mz, first, 1.0, warp, lane);
         for (int e = tid; e < D * Mz; e += NTHREADS) {
             const int d = e / Mz, m = e % Mz;
             double s = 0.0;
@@ -334,11 +375,19 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
         __syncthreads();
-        for (int m = warp; m < Mz; m += NTHREADS / 32) {
-            const double* pr = Pbar + (size_t)m * Mz;
-            double s = 0.0;
-            for (int k = 0; k < Mz; ++k) s += pr[k] * Vs[k * LDS_ + lane];
-            Us[m * LDS_ + lane] = s;
+        for (int m0 = SP_RB * warp; m0 < Mz; m0 += SP_RB * (NTHREADS / 32)) {
+            const double* pr[SP_RB];
+            double sacc[SP_RB];
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r) { pr[r] = Pbar + (size_t)min(m0 + r, Mz - 1) * Mz; sacc[r] = 0.0; }
+            for (int k = 0; k < Mz; ++k) {
+                const double x = Vs[k * LDS_ + lane];
+#pragma unroll
+                for (int r = 0; r < SP_RB; ++r) sacc[r] += pr[r][k] * x;
+            }
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r)
+                if (m0 + r < Mz) Us[(m0 + r) * LDS_ + lane] = sacc[r];
         }
         __syncthreads();
         if (tid < SP_SL && !empty && j0 + tid < M) {
@@ -365,11 +414,19 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         }
         __syncthreads();
         // Kuf_bar[k][j] = sum_{m >= k} Linv[m][k] Vbar[m][j]
-        for (int k = warp; k < Mz; k += NTHREADS / 32) {
-            const double* lc = LinvT + (size_t)k * Mz;
-            double s = 0.0;
-            for (int m = k; m < Mz; ++m) s += lc[m] * Us[m * LDS_ + lane];
-            Gs[k * LDS_ + lane] = s;
+        for (int k0 = SP_RB * warp; k0 < Mz; k0 += SP_RB * (NTHREADS / 32)) {   // LinvT rows are zero left of the diagonal
+            const double* lc[SP_RB];
+            double sacc[SP_RB];
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r) { lc[r] = LinvT + (size_t)min(k0 + r, Mz - 1) * Mz; sacc[r] = 0.0; }
+            for (int m = k0; m < Mz; ++m) {
+                const double x = Us[m * LDS_ + lane];
+#pragma unroll
+                for (int r = 0; r < SP_RB; ++r) sacc[r] += lc[r][m] * x;
+            }
+#pragma unroll
+            for (int r = 0; r < SP_RB; ++r)
+                if (k0 + r < Mz) Gs[(k0 + r) * LDS_ + lane] = sacc[r];
         }
         __syncthreads();
         // hyper-gradient through K(Z, X)
@@ -393,14 +450,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
                 }
             }
         // Lbar partial = -tril(Kuf_bar V^T)
-        for (int m = warp; m < Mz; m += NTHREADS / 32)
-            for (int n = lane; n <= m; n += 32) {
-                double s = 0.0;
-#pragma unroll 8
-                for (int jj = 0; jj < SP_SL; ++jj) s += Gs[m * LDS_ + jj] * Vs[n * LDS_ + jj];
-                double* dst = Lp + (size_t)m * Mz + n;
-                *dst = first ? -s : (*dst - s);
-            }
+        slab_outer_lower(Gs, Vs, Lp, Mz, first, -1.0, warp, lane);
         first = false;
     }
     adel = block_sum(adel, red);

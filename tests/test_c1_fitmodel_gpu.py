@@ -23,14 +23,17 @@ def _evidence(loglik, grid):
 
 
 @pytest.mark.parametrize("which,fix", [("train", False), ("fixed", True)])
-@pytest.mark.parametrize("driver", ["FitModel", "FitModelBatch"])
+@pytest.mark.parametrize("driver", ["FitModel", "FitModelBatch", "FitModel(optimizer=device)"])
 def test_c1_fitmodel_matches_oracle_golden(which, fix, driver):
     from branchedgp_b200 import FitBranchingModel
     t, Y, labels, grid = c1_problem()
     if driver == "FitModel":
         d = FitBranchingModel.FitModel(grid, t, Y, labels, M=0, maxiter=MAXITER, fixHyperparameters=fix, fPredict=False)
-    else:
+    elif driver == "FitModelBatch":
         d = FitBranchingModel.FitModelBatch(grid, t, Y, labels, M=0, maxiter=MAXITER, fixHyperparameters=fix, fPredict=False)[0]
+    else:
+        d = FitBranchingModel.FitModel(grid, t, Y, labels, M=0, maxiter=MAXITER, fixHyperparameters=fix, fPredict=False, optimizer="device")
+        assert set(d) == {"loglik", "Phi", "prediction", "hyperparameters", "posteriorB"}
     ll, want = d["loglik"], GOLD[which + "/loglik"]
     assert np.all(np.isfinite(ll))
     assert int(np.argmax(ll)) == int(np.argmax(want))
