@@ -35,7 +35,9 @@ def main():
                           cycles_per_kstep=round(v[3] / max(v[5], 1), 1), ideal_cycles_per_kstep=8192,
                           frac_wait_first_stages=round(v[0] / max(v[3], 1), 4),
                           frac_wait_later_stages=round(v[1] / max(v[3], 1), 4),
-                          frac_producer_wait_empty=round(v[2] / max(v[3], 1), 4))))
+                          frac_producer_wait_empty=round(v[2] / max(v[3], 1), 4),
+                          chol128_us_per_block=round(v[6] / 1.965e3 / (2 * ctas * ((3 * N + 127) // 128)), 2),
+                          trinv128_us_per_block=round(v[7] / 1.965e3 / (2 * ctas * ((3 * N + 127) // 128)), 2))))
 
 
 if __name__ == "__main__":
