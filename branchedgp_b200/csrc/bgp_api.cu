@@ -58,6 +58,7 @@ SlotLayout slot_layout(const DenseDims& d) {
     L.klpart = take(d.nch);
     L.lse = take(d.N);
     L.klrow = take((size_t)d.N * PHI_KLW);
+    L.rowpart = take((size_t)d.N * phi_col_chunks(d.M));
     L.total = o;
     return L;
 }
@@ -169,6 +170,8 @@ int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const dou
     F.lse = (double*)(base + SL.lse); F.Apart = (double*)(base + SL.Apart); F.vpart = (double*)(base + SL.vpart);
     F.klpart = (double*)(base + SL.klpart);
     F.klrow = (double*)(base + SL.klrow);
+    F.rowpart = (double*)(base + SL.rowpart);
+    F.rch = PHI_RCH;
     F.slot_stride = (long long)stride_d;
     const VecLayout VL = vec_layout(d.Mp, d.nM, D);
     F.Abar = P.vec + VL.Abar; F.vbar = P.vec + VL.vbar;
@@ -397,7 +400,9 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int SD = multi ? Dtot : 1, D = multi ? 1 : Dtot;
     const int M = 3 * N, Mp = (M + SP_SL - 1) / SP_SL * SP_SL;
-    const int nch = (N + PHI_RCH - 1) / PHI_RCH;
+    // rows per chunk of the assignment-pass partials: the streaming passes (long rows, bound + gradient) take larger chunks
+    const int rch = phi_streaming(N, M, SD, D, want_grad != 0, PHI_SRCH) ? PHI_SRCH : PHI_RCH;
+    const int nch = (N + rch - 1) / rch;
     const int nslab = Mp / SP_SL;
     // items per wave: bounded by memory; column splits so that a wave fills the GPU about twice
     auto slot_bytes_for = [&](int nsplit) { return (size_t)sparse_layout(N, Mp, Mz, D, nsplit, nch).total * 8; };
@@ -430,10 +435,11 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
 
     PhiParams F;
     memset(&F, 0, sizeof(F));
-    F.N = N; F.M = M; F.Mp = Mp; F.D = D; F.nch = nch; F.model = model; F.kl_weight = 1.0; F.SD = SD; F.Dtot = Dtot;
+    F.N = N; F.M = M; F.Mp = Mp; F.D = D; F.nch = nch; F.rch = rch; F.model = model; F.kl_weight = 1.0; F.SD = SD; F.Dtot = Dtot;
     F.slot_stride = SL.total;
     F.logPhi = logPhi; F.t = t; F.prior = prior; F.bv = b; F.Y = Y; F.item_gene = item_gene;
     F.lse = wsd + SL.lse; F.Apart = wsd + SL.Apart; F.vpart = wsd + SL.vpart; F.klpart = wsd + SL.klpart; F.klrow = wsd + SL.klrow;
+    F.rowpart = wsd + SL.rowpart;
     F.Abar = wsd + SL.Abar; F.vbar = wsd + SL.vbar; F.grad_logPhi = grad_logPhi;
 
     for (int item0 = 0; item0 < count; item0 += items_cap) {

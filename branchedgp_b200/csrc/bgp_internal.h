@@ -59,7 +59,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 bgp::DenseDims make_dims(int N, int D);
 
 struct SlotLayout {   // byte offsets inside one slot
-    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, klrow, total;
+    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, klrow, rowpart, total;
 };
 SlotLayout slot_layout(const bgp::DenseDims& d);
 int ensure_ws(bgp_handle* h, size_t bytes);

@@ -8,6 +8,7 @@
 // backward (SURVEY.md App. B.1 last line):
 //     Sbar = a (Abar_j + sum_d Y_id vbar_jd - w (log Phi + 1 - log pZ));  dlogPhi = S (Sbar - sum_k S_ik Sbar_ik)
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "bgp_dense.cuh"
 #include "bgp_math.cuh"
@@ -398,6 +399,288 @@ __global__ void __launch_bounds__(BT, MINB) k_phi_backward_rows(PhiParams P) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------ streaming passes
+// Rows too long for the registers of a CTA (M > 6144: the N = 10 000 inducing-point configuration has 30 000 columns) in bound +
+// gradient calls with one sub-problem and one output per item (every BGP FitModel call).  Nothing is row resident; every pass is
+// a plain stream over the N x M matrix with all of the GPU's warps busy, and the row-wide quantities travel through small
+// per-(column chunk, row) partial arrays that are summed in a fixed order (deterministic):
+//   k_phi_lse_stream  CTA per row, read logPhi once: online (max, sum exp) -> row log-sum-exp                       8 B / element
+//   k_phi_fwd_stream  CTA = 1024 columns x rch rows, thread = 4 columns: S = exp(x - lse) -> stash (gradient buffer), Phi, KL,
+//                     A = sum_i Phi, v = Phi^T y per column, c_i = sum_j S (log Phi + 1 - log pZ) per row            8 B + 8 B
+//   k_phi_kl_stream   KL partials of the column chunks summed per row chunk
+//   k_phi_rsum_stream r_i = sum_j S Sbar = a (sum_j S (Abar_j + y_i vbar_j) - w c_i): reads the stash, no transcendental     8 B
+//   k_phi_bwd_stream  dlogPhi = S (Sbar - r_i) written over the stash, one log per element                           8 B + 8 B
+// 40 B of DRAM traffic, two exps and two logs per element against 2 x 16 B + partial re-reads, one exp and two logs for the
+// row-resident kernels -- which at these row lengths run at a quarter of the issue rate (cluster-wide reductions between the
+// load, compute and store phases of a CTA, two CTAs per SM).
+constexpr int SW = NTHREADS / 32;            // warps per CTA
+constexpr int SCPT = PHI_SCOLS / NTHREADS;   // columns per thread
+
+__device__ __forceinline__ void lse_merge(double& m, double& s, double m2, double s2) {
+    const double mx = fmax(m, m2);
+    s = s * exp(m - mx) + s2 * exp(m2 - mx);
+    m = mx;
+}
+
+__global__ void __launch_bounds__(NTHREADS) k_phi_lse_stream(PhiParams P) {
+    __shared__ double ms[SW], ss[SW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x, slot = blockIdx.y, item = P.item0 + slot;
+    const int M = P.M;
+    const double* x = P.logPhi + ((size_t)item * P.N + row) * M;
+    constexpr int U = 4;
+    double m = -1.0e308, s = 0.0;
+    for (int j0 = tid; j0 < M; j0 += NTHREADS * U) {
+        double v[U];
+        double lm = -1.0e308;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int j = j0 + k * NTHREADS;
+            v[k] = (j < M) ? x[j] : -1.0e308;
+            lm = fmax(lm, v[k]);
+        }
+        if (lm > m) { s *= fast_exp(m - lm); m = lm; }   // rescale the running sum (rare after the first blocks)
+#pragma unroll
+        for (int k = 0; k < U; ++k) s += (j0 + k * NTHREADS < M) ? fast_exp(v[k] - m) : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge(m, s, m2, s2);
+    }
+    if (lane == 0) { ms[warp] = m; ss[warp] = s; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < SW; ++w) lse_merge(m, s, ms[w], ss[w]);
+        P.lse[(size_t)slot * P.slot_stride + row] = m + log(s);
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3) k_phi_fwd_stream(PhiParams P) {
+    __shared__ double lse_s[PHI_SRCH], y_s[PHI_SRCH], cw[SW][PHI_SRCH], red[32];
+    __shared__ int act_s[PHI_SRCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cc = blockIdx.x, chunk = blockIdx.y, slot = blockIdx.z, item = P.item0 + slot;
+    const int N = P.N, M = P.M, Mp = P.Mp, rch = P.rch, ncc = gridDim.x;
+    const int r0 = chunk * rch, nr = min(rch, N - r0);
+    const int jb = cc * PHI_SCOLS + tid;
+    const int model = P.model;
+    const double* prior = P.prior;
+    const double log_eps = log(1e-6);
+    const double b = P.bv[item];
+    const double* lp = P.logPhi + ((size_t)item * N + r0) * M;
+    double* stash = P.grad_logPhi + ((size_t)item * N + r0) * M;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    if (tid < nr) {
+        lse_s[tid] = P.lse[(size_t)slot * P.slot_stride + r0 + tid];
+        y_s[tid] = Yg[(size_t)(r0 + tid) * P.Dtot];
+        act_s[tid] = P.t[r0 + tid] > b ? 1 : 0;
+    }
+    __syncthreads();
+    double a[SCPT], v[SCPT], xn[SCPT];
+    double kl = 0.0;
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        a[k] = 0.0; v[k] = 0.0;
+        const int j = jb + k * NTHREADS;
+        xn[k] = (j < M) ? lp[j] : 0.0;
+    }
+    for (int rr = 0; rr < nr; ++rr) {
+        double x[SCPT];
+#pragma unroll
+        for (int k = 0; k < SCPT; ++k) x[k] = xn[k];
+        if (rr + 1 < nr) {   // next row's elements are in flight while this row's are worked on
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) {
+                const int j = jb + k * NTHREADS;
+                if (j < M) xn[k] = lp[(size_t)(rr + 1) * M + j];
+            }
+        }
+        const int row = r0 + rr;
+        const double l = lse_s[rr], y = y_s[rr];
+        const bool act = act_s[rr] != 0;
+        double c = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCPT; ++k) {
+            const int j = jb + k * NTHREADS;
+            if (j < M) {
+                const double S = fast_exp(x[k] - l);
+                stash[(size_t)rr * M + j] = S;
+                const int f = j - 3 * row;
+                const bool inblock = (f >= 0 && f < 3);
+                const double phi = phi_of(model, act, inblock, f, S);
+                const double d = fast_log(phi) - log_pz(model, act, inblock, f, prior, row, log_eps);
+                a[k] += phi;
+                v[k] = fma(phi, y, v[k]);
+                kl = fma(phi, d, kl);
+                c = fma(S, d + 1.0, c);
+            }
+        }
+        c = warp_sum(c);
+        if (lane == 0) cw[warp][rr] = c;
+    }
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        const int j = jb + k * NTHREADS;
+        if (j < Mp) {
+            P.Apart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = a[k];
+            P.vpart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = v[k];
+        }
+    }
+    kl = block_sum(kl, red);   // (contains the __syncthreads that publishes cw)
+    if (tid == 0) P.klrow[(size_t)slot * P.slot_stride + (size_t)chunk * ncc + cc] = kl;
+    if (tid < nr) {
+        double c = 0.0;
+        for (int w = 0; w < SW; ++w) c += cw[w][tid];
+        P.rowpart[(size_t)slot * P.slot_stride + (size_t)cc * N + r0 + tid] = c;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS) k_phi_kl_stream(PhiParams P, int ncc) {
+    const int slot = blockIdx.x;
+    for (int ch = threadIdx.x; ch < P.nch; ch += NTHREADS) {
+        double kl = 0.0;
+        for (int c = 0; c < ncc; ++c) kl += P.klrow[(size_t)slot * P.slot_stride + (size_t)ch * ncc + c];
+        P.klpart[(size_t)slot * P.slot_stride + ch] = kl;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3) k_phi_rsum_stream(PhiParams P) {
+    __shared__ double y_s[PHI_SRCH], cw[SW][PHI_SRCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cc = blockIdx.x, chunk = blockIdx.y, slot = blockIdx.z, item = P.item0 + slot;
+    const int N = P.N, M = P.M, rch = P.rch;
+    const int r0 = chunk * rch, nr = min(rch, N - r0);
+    const int jb = cc * PHI_SCOLS + tid;
+    const double* S = P.grad_logPhi + ((size_t)item * N + r0) * M;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* Abar = P.Abar + (size_t)slot * P.slot_stride;
+    const double* vbar = P.vbar + (size_t)slot * P.slot_stride;
+    if (tid < nr) y_s[tid] = Yg[(size_t)(r0 + tid) * P.Dtot];
+    double ab[SCPT], vb[SCPT];
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        const int j = jb + k * NTHREADS;
+        ab[k] = (j < M) ? Abar[j] : 0.0;
+        vb[k] = (j < M) ? vbar[j] : 0.0;
+    }
+    __syncthreads();
+    constexpr int RU = 4;   // rows in flight per thread
+    for (int rb = 0; rb < nr; rb += RU) {
+        double s[RU][SCPT];
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) {
+                const int j = jb + k * NTHREADS;
+                s[u][k] = (rb + u < nr && j < M) ? S[(size_t)(rb + u) * M + j] : 0.0;
+            }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (rb + u < nr) {
+                const double y = y_s[rb + u];
+                double p = 0.0;
+#pragma unroll
+                for (int k = 0; k < SCPT; ++k) p = fma(s[u][k], fma(y, vb[k], ab[k]), p);
+                p = warp_sum(p);
+                if (lane == 0) cw[warp][rb + u] = p;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < nr) {
+        double p = 0.0;
+        for (int w = 0; w < SW; ++w) p += cw[w][tid];
+        double* rp = P.rowpart + (size_t)slot * P.slot_stride + (size_t)cc * N + r0 + tid;
+        *rp = SQ_A * (p - P.kl_weight * *rp);
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3) k_phi_bwd_stream(PhiParams P) {
+    __shared__ double r_s[PHI_SRCH], y_s[PHI_SRCH];
+    __shared__ int act_s[PHI_SRCH];
+    const int tid = threadIdx.x;
+    const int cc = blockIdx.x, chunk = blockIdx.y, slot = blockIdx.z, item = P.item0 + slot;
+    const int N = P.N, M = P.M, rch = P.rch, ncc = gridDim.x;
+    const int r0 = chunk * rch, nr = min(rch, N - r0);
+    const int jb = cc * PHI_SCOLS + tid;
+    const int model = P.model;
+    const double* prior = P.prior;
+    const double log_eps = log(1e-6);
+    const double klw = P.kl_weight;
+    const double b = P.bv[item];
+    double* g = P.grad_logPhi + ((size_t)item * N + r0) * M;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* Abar = P.Abar + (size_t)slot * P.slot_stride;
+    const double* vbar = P.vbar + (size_t)slot * P.slot_stride;
+    if (tid < nr) {
+        double r = 0.0;
+        for (int c = 0; c < ncc; ++c) r += P.rowpart[(size_t)slot * P.slot_stride + (size_t)c * N + r0 + tid];
+        r_s[tid] = r;
+        y_s[tid] = Yg[(size_t)(r0 + tid) * P.Dtot];
+        act_s[tid] = P.t[r0 + tid] > b ? 1 : 0;
+    }
+    double ab[SCPT], vb[SCPT], sn[SCPT];
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        const int j = jb + k * NTHREADS;
+        ab[k] = (j < M) ? Abar[j] : 0.0;
+        vb[k] = (j < M) ? vbar[j] : 0.0;
+        sn[k] = (j < M) ? g[j] : 0.0;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+        double s[SCPT];
+#pragma unroll
+        for (int k = 0; k < SCPT; ++k) s[k] = sn[k];
+        if (rr + 1 < nr) {
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) {
+                const int j = jb + k * NTHREADS;
+                if (j < M) sn[k] = g[(size_t)(rr + 1) * M + j];
+            }
+        }
+        const int row = r0 + rr;
+        const double r = r_s[rr], y = y_s[rr];
+        const bool act = act_s[rr] != 0;
+        if (model != MODEL_BGP && !act) {   // MBGP trunk rows use the constant phiTrunk and carry no gradient
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) {
+                const int j = jb + k * NTHREADS;
+                if (j < M) g[(size_t)rr * M + j] = 0.0;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < SCPT; ++k) {
+            const int j = jb + k * NTHREADS;
+            if (j < M) {
+                const int f = j - 3 * row;
+                const bool inblock = (f >= 0 && f < 3);
+                const double phi = fma(SQ_A, s[k], SQ_B);
+                const double lpz = log_pz(model, model == MODEL_BGP ? act : true, inblock, f, prior, row, log_eps);
+                const double sb = SQ_A * (fma(y, vb[k], ab[k]) - klw * (fast_log(phi) + 1.0 - lpz));
+                g[(size_t)rr * M + j] = s[k] * (sb - r);
+            }
+        }
+    }
+}
+
+static bool stream_enabled() {   // BGP_PHI_STREAM=0 keeps long rows on the row-resident / two-pass kernels (A/B timing, tests)
+    const char* e = getenv("BGP_PHI_STREAM");
+    return !(e && e[0] == '0');
+}
+bool phi_streaming(int N, int M, int SD, int D, bool want_grad, int rch) {
+    if (!stream_enabled() || !want_grad || SD != 1 || D != 1 || M <= 512 * 12) return false;
+    const long long nch = (N + rch - 1) / rch;
+    return nch * phi_col_chunks(M) <= (long long)N * PHI_KLW;   // the KL partials live in klrow
+}
+static bool params_streaming(const PhiParams& P) {
+    const int rch = P.rch > 0 ? P.rch : PHI_RCH;
+    return rch <= PHI_SRCH && phi_streaming(P.N, P.M, P.SD, P.D, P.grad_logPhi != nullptr, rch) && P.rowpart != nullptr;
+}
+
 template <int BT, int EPT, int MINB, int CL>
 static void launch_rows_cluster(const PhiParams& P, int nitems, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
@@ -416,6 +699,13 @@ static void launch_rows_cluster(const PhiParams& P, int nitems, cudaStream_t st)
 
 void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
     dim3 grid(P.nch, nsubs);
+    if (params_streaming(P)) {
+        const int ncc = phi_col_chunks(P.M);
+        k_phi_lse_stream<<<dim3(P.N, nsubs), NTHREADS, 0, st>>>(P);
+        k_phi_fwd_stream<<<dim3(ncc, P.nch, nsubs), NTHREADS, 0, st>>>(P);
+        k_phi_kl_stream<<<nsubs, NTHREADS, 0, st>>>(P, ncc);
+        return;
+    }
     // Row pass + column pass through the stash for rows that fit one CTA's registers.  The cluster variants of the row pass
     // (k_phi_rowpass<512, 8, 2, 4 or 8> under a cluster launch) work but were slower than k_phi_forward at N = 10 000 (39 ms against 30 ms for 8 items:
     // two block reductions and a cluster exchange per 4096 elements), so long rows stay with k_phi_forward.
@@ -432,6 +722,12 @@ void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
 }
 void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
     dim3 rows(P.N, nitems);
+    if (params_streaming(P)) {
+        const dim3 grid(phi_col_chunks(P.M), P.nch, nitems);
+        k_phi_rsum_stream<<<grid, NTHREADS, 0, st>>>(P);
+        k_phi_bwd_stream<<<grid, NTHREADS, 0, st>>>(P);
+        return;
+    }
     const bool simple = (P.SD == 1 && P.D == 1);
     if (P.M <= 256 * 4) {
         if (simple) k_phi_backward_rows<256, 4, 4, 1, true><<<rows, 256, 0, st>>>(P);

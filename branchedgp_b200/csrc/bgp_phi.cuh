@@ -6,6 +6,12 @@ namespace bgp {
 
 constexpr int PHI_RCH = 16;   // rows of logPhi handled by one CTA of the forward pass
 constexpr int PHI_KLW = 8;    // KL partials kept per row by the row-resident forward pass (one per CTA of the row's cluster)
+// Streaming passes (rows too long for a CTA's registers, bound + gradient calls of single-output BGP items): a CTA covers
+// PHI_SCOLS columns x rch rows, rch = PHI_SRCH where the caller sizes its partial arrays for it (inducing-point path), else PHI_RCH.
+constexpr int PHI_SCOLS = 1024;
+constexpr int PHI_SRCH = 64;
+inline int phi_col_chunks(int M) { return (M + PHI_SCOLS - 1) / PHI_SCOLS; }
+bool phi_streaming(int N, int M, int SD, int D, bool want_grad, int rch);
 
 // A "sub-problem" is one (work item, output group): dense / sparse BGP have one per item carrying all D outputs
 // (SD = 1, D = Dtot); the MBGP multi-output bound has one per output (SD = Dtot, D = 1) because the trunk mask
@@ -13,6 +19,7 @@ constexpr int PHI_KLW = 8;    // KL partials kept per row by the row-resident fo
 // one item are contiguous.
 struct PhiParams {
     int N, M, Mp, D, nch, model;
+    int rch;                   // rows per chunk of the partial arrays (nch = ceil(N / rch)); 0 means PHI_RCH
     int SD, Dtot;              // sub-problems per item; outputs per item (row length of Y)
     int item0;
     long long slot_stride;     // doubles between consecutive slots for lse / Apart / vpart / klpart / Abar / vbar
@@ -28,7 +35,8 @@ struct PhiParams {
     double* Apart;             // [slot][nch][Mp]
     double* vpart;             // [slot][nch][D][Mp]
     double* klpart;            // [slot][nch]
-    double* klrow;             // [slot][N][PHI_KLW]  scratch of the row-resident forward pass
+    double* klrow;             // [slot][N][PHI_KLW]  scratch of the row-resident forward pass (streaming: [nch][column chunks] KL partials)
+    double* rowpart;           // [slot][column chunks][N]  per-row partial sums of the streaming passes
     // backward inputs (per slot) and output
     const double* Abar;        // [Mp]
     const double* vbar;        // [D][Mp]

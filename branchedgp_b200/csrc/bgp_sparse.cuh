@@ -10,7 +10,7 @@ constexpr int SP_MAX_MZ = 208;     // packed lower triangle of Mz x Mz must fit 
 
 struct SparseLayout {   // offsets in doubles inside one sub-problem slot
     long long L, Linv, LinvT, Ppart, R, Rinv, Pbar, Lbpart, T, W, S, V, A, Delta, v, Abar, vbar, zpart, z, c, q, zbar,
-        kax, dkalx, dkabx, kaz, dkalz, dkabz, scal, hpart, Apart, vpart, klpart, lse, klrow, total;
+        kax, dkalx, dkabx, kaz, dkalz, dkabz, scal, hpart, Apart, vpart, klpart, lse, klrow, rowpart, total;
 };
 
 enum { SS_KL = 0, SS_SUMY2, SS_LOGDET, SS_SUMC2, SS_TRACE, SS_ADELTA, SS_SUMA, SS_COUNT = 8 };
@@ -35,6 +35,7 @@ __host__ __device__ inline SparseLayout sparse_layout(int N, int Mp, int Mz, int
     L.hpart = take((long long)nsplit * 8);     // per split: trace, Adelta, g_ell, g_var, g_b
     L.Apart = take((long long)nch * Mp); L.vpart = take((long long)nch * D * Mp); L.klpart = take(nch); L.lse = take(N);
     L.klrow = take((long long)N * 8);   // PHI_KLW per-row KL partials of the row-resident assignment pass
+    L.rowpart = take((long long)N * ((3 * N + 1023) / 1024));   // [column chunks][N] of the streaming assignment passes
     L.total = (o + 31) & ~31LL;
     return L;
 }

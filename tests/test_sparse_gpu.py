@@ -107,3 +107,29 @@ def test_c3_shape_sparse_bgp_large_n(engine):
     scale = max(abs(g["ell"]), abs(g["var"]), abs(g["likvar"]))
     for j, nm in enumerate(("ell", "var", "likvar")):
         assert abs(out["grad_hyp"][0, j] - g[nm]) <= GRAD_RTOL * max(abs(g[nm]), 1e-3 * scale), (nm, out["grad_hyp"][0, j], g[nm])
+
+
+def test_long_rows_streaming_and_row_resident_passes_agree(engine, monkeypatch):
+    """Rows longer than 6144 columns (N > 2048) take the streaming assignment passes in bound + gradient calls
+    (csrc/bgp_phi.cu); BGP_PHI_STREAM=0 keeps them on the two-pass forward / cluster backward kernels.  Both against the
+    oracle, ragged edges in both directions (N = 2500: last row chunk of 4 rows, last column chunk of 332 columns), two items."""
+    N = 2500
+    pr = make_problem(N, D=1, n_genes=2, bs=(0.6,), seed=81)
+    Z = _Z(30)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BGP_PHI_STREAM", flag)
+        outs.append(engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"]))
+    monkeypatch.delenv("BGP_PHI_STREAM")
+    for k in range(pr["count"]):
+        b, h = pr["b"][k], pr["hyp"][k]
+        e, g = bgp_numpy.sparse_value_and_grad(pr["logPhi"][k], pr["Y"][pr["item_gene"][k]], pr["X"], Z, _pz(pr, b), b, h[0], h[1], h[2])
+        for out in outs:
+            assert out["status"][k] == 0
+            assert abs(out["elbo"][k] - e) <= ELBO_RTOL * abs(e), (out["elbo"][k], e)
+            assert relerr(out["grad_logPhi"][k], g["logPhi"]) <= GRAD_RTOL
+            scale = max(abs(g["ell"]), abs(g["var"]), abs(g["likvar"]))
+            for j, nm in enumerate(("ell", "var", "likvar")):
+                assert abs(out["grad_hyp"][k, j] - g[nm]) <= GRAD_RTOL * max(abs(g[nm]), 1e-3 * scale)
+        assert abs(outs[0]["elbo"][k] - outs[1]["elbo"][k]) <= 1e-12 * abs(e)
+        assert relerr(outs[0]["grad_logPhi"][k], outs[1]["grad_logPhi"][k]) <= 1e-11
