@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_lse_stream(PhiParams P) {
         }
         if (lm > m) { s *= fast_exp(m - lm); m = lm; }   // rescale the running sum (rare after the first blocks)
 #pragma unroll
-        for (int k = 0; k < U; ++k) s += (j0 + k * NTHREADS < M) ? fast_exp(v[k] - m) : 0.0;
+        for (int k = 0; k < U; ++k) s += fast_exp(v[k] - m);   // padding (-1e308) contributes exactly 0
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -667,6 +667,257 @@ __global__ void __launch_bounds__(NTHREADS, 3) k_phi_bwd_stream(PhiParams P) {
     }
 }
 
+
+// ---- BGP specialisations of the two heavy streams: branch-free element code.  Phi = a S + b everywhere, log pZ = log 1e-6 for
+// every element outside the 3 own-cell columns of a row; those (at most 3 per row, in one column chunk) are patched by the row's
+// thread after the main loop, so the hot loop has no data-dependent branch and the four elements of a thread interleave.
+template <bool FULL>
+__device__ __forceinline__ void fwd_row_bgp(const double (&x)[SCPT], double* __restrict__ st, int jb, int M, double l, double y,
+                                            double log_eps, double (&a)[SCPT], double (&v)[SCPT], double& kl, double& c) {
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        const int j = jb + k * NTHREADS;
+        if (FULL || j < M) {
+            const double S = fast_exp(x[k] - l);
+            st[k * NTHREADS] = S;
+            const double phi = fma(SQ_A, S, SQ_B);
+            const double d = fast_log(phi) - log_eps;
+            a[k] += phi;
+            v[k] = fma(phi, y, v[k]);
+            kl = fma(phi, d, kl);
+            c = fma(S, d + 1.0, c);
+        }
+    }
+}
+
+// TMA = true (rows start 16-byte aligned, i.e. M even): the CTA's 8 KB piece of each row arrives through cp.async.bulk in a ring of
+// SNST stages filled SNST - 1 rows ahead by thread 0 (full / empty mbarriers, one empty arrival per warp), so 3 CTAs keep
+// 72 KB per SM in flight without spending registers on it; TMA = false: register prefetch of the next row.
+constexpr int SNST = 4;
+struct StreamRing {
+    double* ring;      // [SNST][PHI_SCOLS]
+    uint64_t* full;    // [SNST]
+    uint64_t* empty;   // [SNST]
+    const double* src; // element (row 0, column c0) of this CTA's block
+    uint32_t bytes;    // per row
+    int M, nr;
+    __device__ __forceinline__ void init(int tid) {
+        if (tid == 0) {
+            for (int s = 0; s < SNST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SW); }
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int r = 0; r < SNST - 1 && r < nr; ++r) issue(r);
+    }
+    __device__ __forceinline__ void issue(int r) {
+        const int s = r % SNST;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        tma_load_1d(ring + (size_t)s * PHI_SCOLS, src + (size_t)r * M, bytes, &full[s]);
+    }
+    // top of iteration rr: refill the stage consumed in iteration rr - 1, then wait for row rr
+    __device__ __forceinline__ const double* acquire(int rr, int tid) {
+        if (tid == 0) {
+            const int nxt = rr + SNST - 1;
+            if (nxt < nr) {
+                if (nxt >= SNST) mbar_wait(&empty[nxt % SNST], (uint32_t)((nxt / SNST - 1) & 1));
+                issue(nxt);
+            }
+        }
+        mbar_wait(&full[rr % SNST], (uint32_t)((rr / SNST) & 1));
+        return ring + (size_t)(rr % SNST) * PHI_SCOLS;
+    }
+    __device__ __forceinline__ void release(int rr, int lane) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[rr % SNST]);
+    }
+};
+
+template <bool TMA>
+__global__ void __launch_bounds__(NTHREADS, 3) k_phi_fwd_stream_bgp(PhiParams P) {
+    __shared__ double lse_s[PHI_SRCH], y_s[PHI_SRCH], cw[SW][PHI_SRCH], red[32];
+    __shared__ int act_s[PHI_SRCH];
+    __shared__ __align__(128) double ring_s[TMA ? SNST * PHI_SCOLS : 1];
+    __shared__ uint64_t bars[2 * SNST];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cc = blockIdx.x, chunk = blockIdx.y, slot = blockIdx.z, item = P.item0 + slot;
+    const int N = P.N, M = P.M, Mp = P.Mp, rch = P.rch, ncc = gridDim.x;
+    const int r0 = chunk * rch, nr = min(rch, N - r0);
+    const int c0 = cc * PHI_SCOLS, jb = c0 + tid;
+    const bool full = c0 + PHI_SCOLS <= M;
+    const double log_eps = log(1e-6);
+    const double b = P.bv[item];
+    const double* lp = P.logPhi + ((size_t)item * N + r0) * M + jb;
+    double* st = P.grad_logPhi + ((size_t)item * N + r0) * M + jb;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    if (tid < nr) {
+        lse_s[tid] = P.lse[(size_t)slot * P.slot_stride + r0 + tid];
+        y_s[tid] = Yg[(size_t)(r0 + tid) * P.Dtot];
+        act_s[tid] = P.t[r0 + tid] > b ? 1 : 0;
+    }
+    __syncthreads();
+    double a[SCPT], v[SCPT], xn[SCPT];
+    double kl = 0.0;
+    StreamRing R;
+    if (TMA) {
+        R.ring = ring_s; R.full = bars; R.empty = bars + SNST; R.src = lp - tid; R.M = M; R.nr = nr;
+        R.bytes = (uint32_t)(min(PHI_SCOLS, M - c0) * 8);
+        R.init(tid);
+    }
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        a[k] = 0.0; v[k] = 0.0;
+        xn[k] = 0.0;
+        if (!TMA && (full || jb + k * NTHREADS < M)) xn[k] = lp[k * NTHREADS];
+    }
+    for (int rr = 0; rr < nr; ++rr) {
+        double x[SCPT];
+        if (TMA) {
+            const double* rowp = R.acquire(rr, tid);
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) x[k] = (full || jb + k * NTHREADS < M) ? rowp[tid + k * NTHREADS] : 0.0;
+            R.release(rr, lane);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) x[k] = xn[k];
+            lp += M;
+            if (rr + 1 < nr) {   // next row's elements are in flight while this row's are worked on
+#pragma unroll
+                for (int k = 0; k < SCPT; ++k)
+                    if (full || jb + k * NTHREADS < M) xn[k] = lp[k * NTHREADS];
+            }
+        }
+        double c = 0.0;
+        if (full) fwd_row_bgp<true>(x, st, jb, M, lse_s[rr], y_s[rr], log_eps, a, v, kl, c);
+        else fwd_row_bgp<false>(x, st, jb, M, lse_s[rr], y_s[rr], log_eps, a, v, kl, c);
+        st += M;
+        c = warp_sum(c);
+        if (lane == 0) cw[warp][rr] = c;
+    }
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        const int j = jb + k * NTHREADS;
+        if (j < Mp) {
+            P.Apart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = a[k];
+            P.vpart[(size_t)slot * P.slot_stride + (size_t)chunk * Mp + j] = v[k];
+        }
+    }
+    __syncthreads();   // the stash values written above are visible to the row threads below
+    if (tid < nr) {
+        const int row = r0 + tid;
+        double c = 0.0;
+        for (int w = 0; w < SW; ++w) c += cw[w][tid];
+        const double* srow = P.grad_logPhi + ((size_t)item * N + row) * M;
+        for (int f = 0; f < 3; ++f) {   // own-cell columns: replace log 1e-6 by the true log pZ
+            const int j = 3 * row + f;
+            if (j >= c0 && j < c0 + PHI_SCOLS) {
+                const double S = srow[j];
+                const double dl = log_eps - log_pz(MODEL_BGP, act_s[tid] != 0, true, f, P.prior, row, log_eps);
+                kl = fma(fma(SQ_A, S, SQ_B), dl, kl);
+                c = fma(S, dl, c);
+            }
+        }
+        P.rowpart[(size_t)slot * P.slot_stride + (size_t)cc * N + row] = c;
+    }
+    kl = block_sum(kl, red);
+    if (tid == 0) P.klrow[(size_t)slot * P.slot_stride + (size_t)chunk * ncc + cc] = kl;
+}
+
+template <bool FULL>
+__device__ __forceinline__ void bwd_row_bgp(const double (&s)[SCPT], double* __restrict__ g, int jb, int M, double r, double y, double klw,
+                                            double log_eps, const double (&ab)[SCPT], const double (&vb)[SCPT]) {
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        if (FULL || jb + k * NTHREADS < M) {
+            const double phi = fma(SQ_A, s[k], SQ_B);
+            const double sb = SQ_A * (fma(y, vb[k], ab[k]) - klw * (fast_log(phi) + 1.0 - log_eps));
+            g[k * NTHREADS] = s[k] * (sb - r);
+        }
+    }
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(NTHREADS, 3) k_phi_bwd_stream_bgp(PhiParams P) {
+    __shared__ double r_s[PHI_SRCH], y_s[PHI_SRCH];
+    __shared__ __align__(128) double ring_s[TMA ? SNST * PHI_SCOLS : 1];
+    __shared__ uint64_t bars[2 * SNST];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cc = blockIdx.x, chunk = blockIdx.y, slot = blockIdx.z, item = P.item0 + slot;
+    const int N = P.N, M = P.M, rch = P.rch, ncc = gridDim.x;
+    const int r0 = chunk * rch, nr = min(rch, N - r0);
+    const int c0 = cc * PHI_SCOLS, jb = c0 + tid;
+    const bool full = c0 + PHI_SCOLS <= M;
+    const double log_eps = log(1e-6);
+    const double klw = P.kl_weight;
+    double* g = P.grad_logPhi + ((size_t)item * N + r0) * M + jb;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* Abar = P.Abar + (size_t)slot * P.slot_stride;
+    const double* vbar = P.vbar + (size_t)slot * P.slot_stride;
+    double sown[3] = {0.0, 0.0, 0.0};   // softmax values of the row's own-cell columns (row thread), saved before they are overwritten
+    if (tid < nr) {
+        double r = 0.0;
+        for (int c = 0; c < ncc; ++c) r += P.rowpart[(size_t)slot * P.slot_stride + (size_t)c * N + r0 + tid];
+        r_s[tid] = r;
+        y_s[tid] = Yg[(size_t)(r0 + tid) * P.Dtot];
+        const int row = r0 + tid;
+        const double* srow = P.grad_logPhi + ((size_t)item * N + row) * M;
+        for (int f = 0; f < 3; ++f) {
+            const int j = 3 * row + f;
+            if (j >= c0 && j < c0 + PHI_SCOLS) sown[f] = srow[j];
+        }
+    }
+    double ab[SCPT], vb[SCPT], sn[SCPT];
+#pragma unroll
+    for (int k = 0; k < SCPT; ++k) {
+        const bool ok = full || jb + k * NTHREADS < M;
+        ab[k] = ok ? Abar[jb + k * NTHREADS] : 0.0;
+        vb[k] = ok ? vbar[jb + k * NTHREADS] : 0.0;
+        sn[k] = (!TMA && ok) ? g[k * NTHREADS] : 0.0;
+    }
+    StreamRing R;
+    if (TMA) {   // (init holds the __syncthreads that orders the own-cell reads above before any write below)
+        R.ring = ring_s; R.full = bars; R.empty = bars + SNST; R.src = g - tid; R.M = M; R.nr = nr;
+        R.bytes = (uint32_t)(min(PHI_SCOLS, M - c0) * 8);
+        R.init(tid);
+    }
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+        double sv[SCPT];
+        if (TMA) {
+            const double* rowp = R.acquire(rr, tid);
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) sv[k] = (full || jb + k * NTHREADS < M) ? rowp[tid + k * NTHREADS] : 0.0;
+            R.release(rr, lane);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCPT; ++k) sv[k] = sn[k];
+            if (rr + 1 < nr) {
+#pragma unroll
+                for (int k = 0; k < SCPT; ++k)
+                    if (full || jb + k * NTHREADS < M) sn[k] = g[(size_t)M + k * NTHREADS];
+            }
+        }
+        if (full) bwd_row_bgp<true>(sv, g, jb, M, r_s[rr], y_s[rr], klw, log_eps, ab, vb);
+        else bwd_row_bgp<false>(sv, g, jb, M, r_s[rr], y_s[rr], klw, log_eps, ab, vb);
+        g += M;
+    }
+    __syncthreads();   // the row threads overwrite elements other threads have just written
+    if (tid < nr) {
+        const int row = r0 + tid;
+        const bool act = P.t[row] > P.bv[item];
+        double* grow = P.grad_logPhi + ((size_t)item * N + row) * M;
+        for (int f = 0; f < 3; ++f) {
+            const int j = 3 * row + f;
+            if (j >= c0 && j < c0 + PHI_SCOLS) {
+                const double S = sown[f];
+                const double lpz = log_pz(MODEL_BGP, act, true, f, P.prior, row, log_eps);
+                const double sb = SQ_A * (fma(y_s[tid], vbar[j], Abar[j]) - klw * (fast_log(fma(SQ_A, S, SQ_B)) + 1.0 - lpz));
+                grow[j] = S * (sb - r_s[tid]);
+            }
+        }
+    }
+}
+
 static bool stream_enabled() {   // BGP_PHI_STREAM=0 keeps long rows on the row-resident / two-pass kernels (A/B timing, tests)
     const char* e = getenv("BGP_PHI_STREAM");
     return !(e && e[0] == '0');
@@ -675,6 +926,12 @@ bool phi_streaming(int N, int M, int SD, int D, bool want_grad, int rch) {
     if (!stream_enabled() || !want_grad || SD != 1 || D != 1 || M <= 512 * 12) return false;
     const long long nch = (N + rch - 1) / rch;
     return nch * phi_col_chunks(M) <= (long long)N * PHI_KLW;   // the KL partials live in klrow
+}
+// bulk copies need 16-byte aligned row pieces: even M and 16-byte aligned buffers (BGP_PHI_TMA=0: register prefetch, for A/B timing)
+static bool stream_tma(const PhiParams& P) {
+    const char* e = getenv("BGP_PHI_TMA");
+    if (e && e[0] == '0') return false;
+    return (P.M % 2 == 0) && ((uintptr_t)P.logPhi % 16 == 0) && ((uintptr_t)P.grad_logPhi % 16 == 0);
 }
 static bool params_streaming(const PhiParams& P) {
     const int rch = P.rch > 0 ? P.rch : PHI_RCH;
@@ -702,7 +959,9 @@ void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
     if (params_streaming(P)) {
         const int ncc = phi_col_chunks(P.M);
         k_phi_lse_stream<<<dim3(P.N, nsubs), NTHREADS, 0, st>>>(P);
-        k_phi_fwd_stream<<<dim3(ncc, P.nch, nsubs), NTHREADS, 0, st>>>(P);
+        if (P.model == MODEL_BGP && stream_tma(P)) k_phi_fwd_stream_bgp<true><<<dim3(ncc, P.nch, nsubs), NTHREADS, 0, st>>>(P);
+        else if (P.model == MODEL_BGP) k_phi_fwd_stream_bgp<false><<<dim3(ncc, P.nch, nsubs), NTHREADS, 0, st>>>(P);
+        else k_phi_fwd_stream<<<dim3(ncc, P.nch, nsubs), NTHREADS, 0, st>>>(P);
         k_phi_kl_stream<<<nsubs, NTHREADS, 0, st>>>(P, ncc);
         return;
     }
@@ -725,7 +984,9 @@ void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
     if (params_streaming(P)) {
         const dim3 grid(phi_col_chunks(P.M), P.nch, nitems);
         k_phi_rsum_stream<<<grid, NTHREADS, 0, st>>>(P);
-        k_phi_bwd_stream<<<grid, NTHREADS, 0, st>>>(P);
+        if (P.model == MODEL_BGP && stream_tma(P)) k_phi_bwd_stream_bgp<true><<<grid, NTHREADS, 0, st>>>(P);
+        else if (P.model == MODEL_BGP) k_phi_bwd_stream_bgp<false><<<grid, NTHREADS, 0, st>>>(P);
+        else k_phi_bwd_stream<<<grid, NTHREADS, 0, st>>>(P);
         return;
     }
     const bool simple = (P.SD == 1 && P.D == 1);

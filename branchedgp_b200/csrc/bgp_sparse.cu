@@ -133,36 +133,84 @@ __device__ __forceinline__ double kuf_entry(const SparseParams& P, const double*
     return (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
 }
 
-constexpr int SP_RB = 4;   // rows per warp pass in the slab products
+// Slab products on the fp64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA): a slab is [Mz][SP_LDS] in shared memory (SP_SL = 32
+// columns of X; SP_LDS = 36 makes both fragment patterns below bank-conflict free: 36 = 4 mod 16 eight-byte banks).
+// lane = 4 g + c:  a = A[g][c],  b = B[c][g],  d = {D[g][2c], D[g][2c + 1]}.
+constexpr int SP_LDS = SP_SL + 4;
+constexpr int SP_WARPS = NTHREADS / 32;
 
-// dst[m][n] (+)= sign * sum_jj A[m][jj] B[n][jj] for n <= m, A / B = [Mz][SP_SL + 1] slabs in shared memory.  Four rows m per warp
-// pass: every B row fetched from shared memory feeds four accumulators.
-__device__ __forceinline__ void slab_outer_lower(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ dst,
+// Cs[m][0..32) = sum_k A[m][k] Bs[k][.],  A = Mz x Mz row-major in global memory (L1 / L2 resident, explicit zeros outside its
+// triangle).  TRI: 0 full, 1 lower (k <= m), 2 upper (k >= m) -- only narrows the k range.  A warp owns two 8-row tiles at a
+// time: 8 independent accumulator tiles hide the DMMA latency, every B fragment feeds two MMAs.
+template <int TRI>
+__device__ __forceinline__ void slab_mm(const double* __restrict__ A, const double* __restrict__ Bs, double* __restrict__ Cs, int Mz,
+                                        int warp, int lane) {
+    const int g = lane >> 2, c = lane & 3;
+    const int nrt = (Mz + 7) >> 3;
+    for (int rt = 2 * warp; rt < nrt; rt += 2 * SP_WARPS) {
+        const int m0 = rt * 8;
+        const int ra = m0 + g, rb = m0 + 8 + g;
+        const bool va = ra < Mz, vb = rb < Mz;
+        const double* pa = A + (size_t)min(ra, Mz - 1) * Mz;
+        const double* pb = A + (size_t)min(rb, Mz - 1) * Mz;
+        double acc[2][4][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { acc[h][t][0] = 0.0; acc[h][t][1] = 0.0; }
+        const int k0 = (TRI == 2) ? m0 : 0;
+        const int k1 = (TRI == 1) ? min(Mz, m0 + 16) : Mz;
+        for (int k = k0; k < k1; k += 4) {
+            const int kk = k + c;
+            const bool vk = kk < Mz;
+            const double a0 = (va && vk) ? pa[kk] : 0.0;
+            const double a1 = (vb && vk) ? pb[kk] : 0.0;
+            const double* bk = Bs + (size_t)min(kk, Mz - 1) * SP_LDS + g;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const double b = vk ? bk[8 * t] : 0.0;
+                dmma(acc[0][t][0], acc[0][t][1], a0, b);
+                dmma(acc[1][t][0], acc[1][t][1], a1, b);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (va) { Cs[(size_t)ra * SP_LDS + 8 * t + 2 * c] = acc[0][t][0]; Cs[(size_t)ra * SP_LDS + 8 * t + 2 * c + 1] = acc[0][t][1]; }
+            if (vb) { Cs[(size_t)rb * SP_LDS + 8 * t + 2 * c] = acc[1][t][0]; Cs[(size_t)rb * SP_LDS + 8 * t + 2 * c + 1] = acc[1][t][1]; }
+        }
+    }
+}
+
+// dst[m][n] (+)= sign * sum_jj As[m][jj] Bs[n][jj] for n <= m (dst = Mz x Mz row-major in global memory, lower triangle).  The 8 x 8
+// tiles of the lower triangle are dealt to the warps one by one; two accumulator chains (even / odd k steps) per tile.
+__device__ __forceinline__ void slab_outer_lower(const double* __restrict__ As, const double* __restrict__ Bs, double* __restrict__ dst,
                                                  int Mz, bool first, double sign, int warp, int lane) {
-    const int LDS_ = SP_SL + 1;
-    for (int m0 = SP_RB * warp; m0 < Mz; m0 += SP_RB * (NTHREADS / 32)) {
-        const int mtop = min(m0 + SP_RB - 1, Mz - 1);
-        const double* ar[SP_RB];
+    const int g = lane >> 2, c = lane & 3;
+    const int nt = (Mz + 7) >> 3;
+    const int ntiles = nt * (nt + 1) / 2;
+    for (int tix = warp; tix < ntiles; tix += SP_WARPS) {
+        int rt = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+        while (rt * (rt + 1) / 2 > tix) --rt;
+        while ((rt + 1) * (rt + 2) / 2 <= tix) ++rt;
+        const int ct = tix - rt * (rt + 1) / 2;
+        const int m = rt * 8 + g, nr = ct * 8 + g;
+        const bool vm = m < Mz, vn = nr < Mz;
+        const double* pa = As + (size_t)min(m, Mz - 1) * SP_LDS + c;
+        const double* pb = Bs + (size_t)min(nr, Mz - 1) * SP_LDS + c;
+        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
-        for (int r = 0; r < SP_RB; ++r) ar[r] = A + (size_t)min(m0 + r, Mz - 1) * LDS_;
-        for (int n = lane; n <= mtop; n += 32) {
-            double sacc[SP_RB];
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r) sacc[r] = 0.0;
-            const double* bn = B + (size_t)n * LDS_;
-#pragma unroll 8
-            for (int jj = 0; jj < SP_SL; ++jj) {
-                const double x = bn[jj];
-#pragma unroll
-                for (int r = 0; r < SP_RB; ++r) sacc[r] += ar[r][jj] * x;
-            }
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r) {
-                const int m = m0 + r;
-                if (m >= Mz || n > m) continue;
-                double* d = dst + (size_t)m * Mz + n;
-                *d = first ? sign * sacc[r] : (*d + sign * sacc[r]);
-            }
+        for (int k = 0; k < SP_SL; k += 8) {
+            const double a0 = vm ? pa[k] : 0.0, b0 = vn ? pb[k] : 0.0;
+            const double a1 = vm ? pa[k + 4] : 0.0, b1 = vn ? pb[k + 4] : 0.0;
+            dmma(d0, d1, a0, b0);
+            dmma(e0, e1, a1, b1);
+        }
+        d0 += e0; d1 += e1;
+        if (vm) {
+            const int n = ct * 8 + 2 * c;
+            double* d = dst + (size_t)m * Mz + n;
+            if (n <= m) d[0] = first ? sign * d0 : (d[0] + sign * d0);
+            if (n + 1 <= m) d[1] = first ? sign * d1 : (d[1] + sign * d1);
         }
     }
 }
@@ -203,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
     SP_SETUP();
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
-    const int LDS_ = SP_SL + 1;
+    constexpr int LDS_ = SP_LDS;
     double* Ks = sm;                       // [Mz][33]  K(Z, x_j) of the slab
     double* Vs = sm + (size_t)Mz * LDS_;   // [Mz][33]  V of the slab
     double* Dls = Vs + (size_t)Mz * LDS_;  // [32] Delta of the slab
@@ -224,29 +272,14 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
         __syncthreads();
-        // four rows per warp pass: four independent accumulators share every shared-memory load of Ks (Linv is stored as a
-        // full square with explicit zeros above the diagonal, so the four rows run over the same k range)
-        for (int m0 = SP_RB * warp; m0 < Mz; m0 += SP_RB * (NTHREADS / 32)) {
-            const double* lr[SP_RB];
-            double sacc[SP_RB];
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r) { lr[r] = Linv + (size_t)min(m0 + r, Mz - 1) * Mz; sacc[r] = 0.0; }
-            const int kend = min(m0 + SP_RB - 1, Mz - 1);
-            for (int k = 0; k <= kend; ++k) {
-                const double x = Ks[k * LDS_ + lane];
-#pragma unroll
-                for (int r = 0; r < SP_RB; ++r) sacc[r] += lr[r][k] * x;
-            }
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r) {
-                const int m = m0 + r;
-                if (m >= Mz) break;
-                Vs[m * LDS_ + lane] = sacc[r];
-                if (!empty && j0 + lane < Mp) ws[SLy.V + (size_t)m * Mp + j0 + lane] = sacc[r];
-                tr += Dls[lane] * sacc[r] * sacc[r];
-            }
-        }
+        slab_mm<1>(Linv, Ks, Vs, Mz, warp, lane);   // V = Linv K(Z, X_slab)
         __syncthreads();
+        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            const int m = e / SP_SL, jj = e % SP_SL;
+            const double x = Vs[m * LDS_ + jj];
+            if (!empty && j0 + jj < Mp) ws[SLy.V + (size_t)m * Mp + j0 + jj] = x;
+            tr += Dls[jj] * x * x;
+        }
         // Ks <- Delta_j V (scaled copy) so that P += Ks Vs^T
         for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
             const int m = e / SP_SL, jj = e % SP_SL;
@@ -352,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
     SP_SETUP();
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
-    const int LDS_ = SP_SL + 1;
+    constexpr int LDS_ = SP_LDS;
     double* Vs = sm;                        // V slab
     double* Us = sm + (size_t)Mz * LDS_;    // U, then Vbar
     double* Gs = Us + (size_t)Mz * LDS_;    // Kuf_bar
@@ -375,35 +408,42 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
         __syncthreads();
-        for (int m0 = SP_RB * warp; m0 < Mz; m0 += SP_RB * (NTHREADS / 32)) {
-            const double* pr[SP_RB];
-            double sacc[SP_RB];
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r) { pr[r] = Pbar + (size_t)min(m0 + r, Mz - 1) * Mz; sacc[r] = 0.0; }
-            for (int k = 0; k < Mz; ++k) {
-                const double x = Vs[k * LDS_ + lane];
-#pragma unroll
-                for (int r = 0; r < SP_RB; ++r) sacc[r] += pr[r][k] * x;
-            }
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r)
-                if (m0 + r < Mz) Us[(m0 + r) * LDS_ + lane] = sacc[r];
+        slab_mm<0>(Pbar, Vs, Us, Mz, warp, lane);   // U = Pbar V
+        __syncthreads();
+        // column sums over the Mz rows: warp w takes rows w, w + 8, ...; the partials are combined through Gs (free until the
+        // next product) when its Mz rows can hold them, else one warp runs over all rows
+        const bool wide = 2 * SP_WARPS <= Mz;
+        const int mstep = wide ? SP_WARPS : 1;
+        if (wide || warp == 0) {
+            double vu = 0.0, vv = 0.0;
+            for (int m = wide ? warp : 0; m < Mz; m += mstep) { const double x = Vs[m * LDS_ + lane]; vu += x * Us[m * LDS_ + lane]; vv += x * x; }
+            if (wide) { Gs[warp * LDS_ + lane] = vu; Gs[(SP_WARPS + warp) * LDS_ + lane] = vv; }
+            else { Gs[lane] = vu; Gs[LDS_ + lane] = vv; }   // Mz >= 2 rows are always there
         }
         __syncthreads();
         if (tid < SP_SL && !empty && j0 + tid < M) {
             const int j = j0 + tid;
             double vu = 0.0, vv = 0.0;
-            for (int m = 0; m < Mz; ++m) { const double x = Vs[m * LDS_ + tid]; vu += x * Us[m * LDS_ + tid]; vv += x * x; }
+            for (int w = 0; w < (wide ? SP_WARPS : 1); ++w) { vu += Gs[w * LDS_ + tid]; vv += Gs[((wide ? SP_WARPS : 1) + w) * LDS_ + tid]; }
             const double dlt = vu + 0.5 * vv - 0.5 * kdiag;
             ws[SLy.Abar + j] = dlt / likvar;
             adel += ws[SLy.A + j] * dlt;
-            for (int d = 0; d < D; ++d) {
-                double s = 0.0;
-                for (int m = 0; m < Mz; ++m) s += Vs[m * LDS_ + tid] * ws[SLy.zbar + (size_t)d * Mz + m];
-                ws[SLy.vbar + (size_t)d * Mp + j] = s;
-            }
         }
         __syncthreads();
+        for (int d = 0; d < D; ++d) {   // vbar = V^T zbar
+            if (wide || warp == 0) {
+                double sacc = 0.0;
+                for (int m = wide ? warp : 0; m < Mz; m += mstep) sacc += Vs[m * LDS_ + lane] * ws[SLy.zbar + (size_t)d * Mz + m];
+                Gs[(wide ? warp : 0) * LDS_ + lane] = sacc;
+            }
+            __syncthreads();
+            if (tid < SP_SL && !empty && j0 + tid < M) {
+                double sacc = 0.0;
+                for (int w = 0; w < (wide ? SP_WARPS : 1); ++w) sacc += Gs[w * LDS_ + tid];
+                ws[SLy.vbar + (size_t)d * Mp + j0 + tid] = sacc;
+            }
+            __syncthreads();
+        }
         // Vbar = 2 Delta U + zbar v^T + Delta V
         for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
@@ -414,20 +454,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         }
         __syncthreads();
         // Kuf_bar[k][j] = sum_{m >= k} Linv[m][k] Vbar[m][j]
-        for (int k0 = SP_RB * warp; k0 < Mz; k0 += SP_RB * (NTHREADS / 32)) {   // LinvT rows are zero left of the diagonal
-            const double* lc[SP_RB];
-            double sacc[SP_RB];
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r) { lc[r] = LinvT + (size_t)min(k0 + r, Mz - 1) * Mz; sacc[r] = 0.0; }
-            for (int m = k0; m < Mz; ++m) {
-                const double x = Us[m * LDS_ + lane];
-#pragma unroll
-                for (int r = 0; r < SP_RB; ++r) sacc[r] += lc[r][m] * x;
-            }
-#pragma unroll
-            for (int r = 0; r < SP_RB; ++r)
-                if (k0 + r < Mz) Gs[(k0 + r) * LDS_ + lane] = sacc[r];
-        }
+        slab_mm<2>(LinvT, Us, Gs, Mz, warp, lane);   // LinvT rows are zero left of the diagonal
         __syncthreads();
         // hyper-gradient through K(Z, X)
         if (!empty)
@@ -636,7 +663,7 @@ void sparse_launch_predict(const SparseParams& P, const double* Xnew, int T, int
 
 // ---------------------------------------------------------------------------------------------------- launchers
 static size_t packed_bytes(int Mz) { return (size_t)Mz * (Mz + 1) / 2 * 8; }
-static size_t slab_bytes(int Mz, int nbuf) { return ((size_t)nbuf * Mz * (SP_SL + 1) + SP_SL) * 8; }
+static size_t slab_bytes(int Mz, int nbuf) { return ((size_t)nbuf * Mz * SP_LDS + SP_SL) * 8; }
 
 cudaError_t sparse_init_kernels() {
     cudaError_t e;
