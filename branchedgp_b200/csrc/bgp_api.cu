@@ -430,6 +430,7 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     P.N = N; P.M = M; P.Mp = Mp; P.Mz = Mz; P.D = D; P.nch = nch; P.nsplit = nsplit; P.SD = SD; P.Dtot = Dtot;
     P.kind = kernel_kind; P.model = model; P.want_grad = want_grad; P.square_noise = 1e-6; P.kl_weight = 1.0;
     P.slot_stride = SL.total;
+    P.lay = SL;
     P.t = t; P.Z = Z; P.hyp = hyp; P.bv = b; P.Y = Y; P.item_gene = item_gene;
     P.ws = wsd; P.status = status; P.elbo = elbo; P.grad_hyp = want_grad ? grad_hyp : nullptr; P.grad_b = want_grad ? grad_b : nullptr;
 

@@ -19,7 +19,7 @@ namespace bgp {
     const int item = P.item0 + slot / P.SD;                                                                   \
     const int sd = slot % P.SD;                                                                               \
     const int Mz = P.Mz, Mp = P.Mp, M = P.M, N = P.N, D = P.D;                                                \
-    const SparseLayout SLy = sparse_layout(N, Mp, Mz, D, P.nsplit, P.nch);                                    \
+    const SparseLayout& SLy = P.lay;                                                                          \
     double* const ws = P.ws + (size_t)slot * P.slot_stride;                                                   \
     const double ell = P.hyp[(size_t)item * 3 + 0], kvar = P.hyp[(size_t)item * 3 + 1], likvar = P.hyp[(size_t)item * 3 + 2]; \
     const double bpt = P.bv[(size_t)item * P.SD + sd];                                                        \
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_reduce_partials(SparseParams P)
     const int slot = blockIdx.y;
     const int item = P.item0 + slot / P.SD;
     const int Mp = P.Mp, M = P.M, D = P.D, nch = P.nch;
-    const SparseLayout SLy = sparse_layout(P.N, Mp, P.Mz, D, P.nsplit, nch);
+    const SparseLayout& SLy = P.lay;
     double* const ws = P.ws + (size_t)slot * P.slot_stride;
     const double likvar = P.hyp[(size_t)item * 3 + 2];
     const int j = blockIdx.x * NTHREADS + threadIdx.x;
@@ -140,43 +140,44 @@ constexpr int SP_LDS = SP_SL + 4;
 constexpr int SP_WARPS = NTHREADS / 32;
 
 // Cs[m][0..32) = sum_k A[m][k] Bs[k][.],  A = Mz x Mz row-major in global memory (L1 / L2 resident, explicit zeros outside its
-// triangle).  TRI: 0 full, 1 lower (k <= m), 2 upper (k >= m) -- only narrows the k range.  A warp owns two 8-row tiles at a
-// time: 8 independent accumulator tiles hide the DMMA latency, every B fragment feeds two MMAs.
+// triangle).  TRI: 0 full, 1 lower (k <= m), 2 upper (k >= m) -- only narrows the k range.
 template <int TRI>
 __device__ __forceinline__ void slab_mm(const double* __restrict__ A, const double* __restrict__ Bs, double* __restrict__ Cs, int Mz,
                                         int warp, int lane) {
     const int g = lane >> 2, c = lane & 3;
     const int nrt = (Mz + 7) >> 3;
-    for (int rt = 2 * warp; rt < nrt; rt += 2 * SP_WARPS) {
-        const int m0 = rt * 8;
-        const int ra = m0 + g, rb = m0 + 8 + g;
-        const bool va = ra < Mz, vb = rb < Mz;
-        const double* pa = A + (size_t)min(ra, Mz - 1) * Mz;
-        const double* pb = A + (size_t)min(rb, Mz - 1) * Mz;
-        double acc[2][4][2];
+    // 8-row tiles dealt to the warps in snake order (w, 15 - w, 16 + w, ...): the triangular k ranges add up evenly
+    for (int i = 0; (i >> 1) * 2 * SP_WARPS < nrt; ++i) {
+        const int base = (i >> 1) * 2 * SP_WARPS;
+        const int rt = (i & 1) ? base + 2 * SP_WARPS - 1 - warp : base + warp;
+        if (rt >= nrt) continue;
+        const int m = rt * 8 + g;
+        const bool vm = m < Mz;
+        const double* pa = A + (size_t)min(m, Mz - 1) * Mz + c;
+        double acc[4][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { acc[h][t][0] = 0.0; acc[h][t][1] = 0.0; }
-        const int k0 = (TRI == 2) ? m0 : 0;
-        const int k1 = (TRI == 1) ? min(Mz, m0 + 16) : Mz;
+        for (int t = 0; t < 4; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        const int k0 = (TRI == 2) ? rt * 8 : 0;
+        const int k1 = (TRI == 1) ? min(Mz, rt * 8 + 8) : Mz;
+        // the A fragments come from global memory (L2): two k steps are kept in flight ahead of the MMAs
+        double an0 = (vm && k0 + c < Mz) ? pa[k0] : 0.0;
+        double an1 = (vm && k0 + 4 + c < Mz) ? pa[k0 + 4] : 0.0;
         for (int k = k0; k < k1; k += 4) {
+            const double a = an0;
+            an0 = an1;
+            an1 = (vm && k + 8 + c < Mz) ? pa[k + 8] : 0.0;
             const int kk = k + c;
             const bool vk = kk < Mz;
-            const double a0 = (va && vk) ? pa[kk] : 0.0;
-            const double a1 = (vb && vk) ? pb[kk] : 0.0;
             const double* bk = Bs + (size_t)min(kk, Mz - 1) * SP_LDS + g;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const double b = vk ? bk[8 * t] : 0.0;
-                dmma(acc[0][t][0], acc[0][t][1], a0, b);
-                dmma(acc[1][t][0], acc[1][t][1], a1, b);
+                dmma(acc[t][0], acc[t][1], a, b);
             }
         }
+        if (vm) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (va) { Cs[(size_t)ra * SP_LDS + 8 * t + 2 * c] = acc[0][t][0]; Cs[(size_t)ra * SP_LDS + 8 * t + 2 * c + 1] = acc[0][t][1]; }
-            if (vb) { Cs[(size_t)rb * SP_LDS + 8 * t + 2 * c] = acc[1][t][0]; Cs[(size_t)rb * SP_LDS + 8 * t + 2 * c + 1] = acc[1][t][1]; }
+            for (int t = 0; t < 4; ++t) { Cs[(size_t)m * SP_LDS + 8 * t + 2 * c] = acc[t][0]; Cs[(size_t)m * SP_LDS + 8 * t + 2 * c + 1] = acc[t][1]; }
         }
     }
 }
@@ -209,8 +210,15 @@ __device__ __forceinline__ void slab_outer_lower(const double* __restrict__ As, 
         if (vm) {
             const int n = ct * 8 + 2 * c;
             double* d = dst + (size_t)m * Mz + n;
-            if (n <= m) d[0] = first ? sign * d0 : (d[0] + sign * d0);
-            if (n + 1 <= m) d[1] = first ? sign * d1 : (d[1] + sign * d1);
+            // every element is owned by this thread for the whole kernel: a plain store on the first slab, then reductions
+            // (RED.ADD.F64, nothing to wait for) in program order -- deterministic
+            if (first) {
+                if (n <= m) d[0] = sign * d0;
+                if (n + 1 <= m) d[1] = sign * d1;
+            } else {
+                if (n <= m) atomicAdd(&d[0], sign * d0);
+                if (n + 1 <= m) atomicAdd(&d[1], sign * d1);
+            }
         }
     }
 }
@@ -266,9 +274,24 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
         const bool empty = sl >= nslab;   // a split without slabs still zero-initialises its partials
         const int j0 = sl * SP_SL;
         __syncthreads();
-        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
-            const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
-            Ks[m * LDS_ + jj] = (!empty && j < M) ? kuf_entry(P, ws, SLy, m, j, ell, kvar, kinv) : 0.0;
+        // K(Z, x_j) of the slab (branch_kernParamGPflow.py:117-198) in two divergence-free sweeps: every (inducing row, cell) pair has
+        // ONE same-function column 3 cell + f_z that needs the base kernel (an exp); all other entries are products of the
+        // per-row / per-cell kernels against the branching point
+        {
+            const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
+            for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+                const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
+                const int cell = j / 3, f = j - 3 * cell;
+                const int fz = (int)P.Z[2 * m + 1] - 1;
+                if (empty || j >= M) Ks[m * LDS_ + jj] = 0.0;
+                else if (fz != f) Ks[m * LDS_ + jj] = (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
+            }
+            if (!empty)
+                for (int e = tid; e < Mz * ncell; e += NTHREADS) {
+                    const int m = e / ncell, cell = cell0 + e % ncell;
+                    const int jj = 3 * cell + (int)P.Z[2 * m + 1] - 1 - j0;
+                    if (jj >= 0 && jj < SP_SL && j0 + jj < M) Ks[m * LDS_ + jj] = kbase(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind);
+                }
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
         __syncthreads();
@@ -456,26 +479,31 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         // Kuf_bar[k][j] = sum_{m >= k} Linv[m][k] Vbar[m][j]
         slab_mm<2>(LinvT, Us, Gs, Mz, warp, lane);   // LinvT rows are zero left of the diagonal
         __syncthreads();
-        // hyper-gradient through K(Z, X)
-        if (!empty)
+        // hyper-gradient through K(Z, X): cross-function entries (products), then the same-function entry of every (row, cell) pair
+        if (!empty) {
             for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
                 const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
                 if (j >= M) continue;
-                const double w = Gs[m * LDS_ + jj];
                 const int cell = j / 3, f = j - 3 * cell;
-                const int fz = (int)P.Z[2 * m + 1] - 1;
-                if (fz == f) {
-                    double k, dl, dd;
-                    kbase_grads(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind, k, dl, dd);
-                    gl += w * dl;
-                    gv += w * k / kvar;
-                } else {
-                    const double a = ws[SLy.kaz + m], b = ws[SLy.kax + cell];
-                    gl += w * (ws[SLy.dkalz + m] * b + a * ws[SLy.dkalx + cell]) * kinv;
-                    gv += w * ((a * kinv) * b) * (2.0 / kvar - kinv);
-                    gb += w * (ws[SLy.dkabz + m] * b + a * ws[SLy.dkabx + cell]) * kinv;
-                }
+                if ((int)P.Z[2 * m + 1] - 1 == f) continue;
+                const double w = Gs[m * LDS_ + jj];
+                const double a = ws[SLy.kaz + m], b = ws[SLy.kax + cell];
+                gl += w * (ws[SLy.dkalz + m] * b + a * ws[SLy.dkalx + cell]) * kinv;
+                gv += w * ((a * kinv) * b) * (2.0 / kvar - kinv);
+                gb += w * (ws[SLy.dkabz + m] * b + a * ws[SLy.dkabx + cell]) * kinv;
             }
+            const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
+            for (int e = tid; e < Mz * ncell; e += NTHREADS) {
+                const int m = e / ncell, cell = cell0 + e % ncell;
+                const int jj = 3 * cell + (int)P.Z[2 * m + 1] - 1 - j0;
+                if (jj < 0 || jj >= SP_SL || j0 + jj >= M) continue;
+                double k, dl, dd;
+                kbase_grads(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind, k, dl, dd);
+                const double w = Gs[m * LDS_ + jj];
+                gl += w * dl;
+                gv += w * k / kvar;
+            }
+        }
         // Lbar partial = -tril(Kuf_bar V^T)
         slab_outer_lower(Gs, Vs, Lp, Mz, first, -1.0, warp, lane);
         first = false;

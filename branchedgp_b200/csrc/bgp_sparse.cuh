@@ -47,6 +47,7 @@ struct SparseParams {
     double square_noise, kl_weight;
     int item0;                          // first ITEM of the wave; slot s <-> sub-problem item0*SD + s
     long long slot_stride;
+    SparseLayout lay;                   // offsets inside a slot (sparse_layout(N, Mp, Mz, D, nsplit, nch), computed once on the host)
     const double* t;         // [N]
     const double* Z;         // [Mz][2]  (time, function 1..3)
     const double* hyp;       // [count][3]

@@ -77,5 +77,9 @@ def run(name, N, Dtot, Mz, count, multi, reps=3):
 
 
 if __name__ == "__main__":
-    run("C3 sparse BGP", 10000, 1, 30, int(sys.argv[1]) if len(sys.argv) > 1 else 8, False)
-    run("C4 MBGP", 500, 100, 180, 4, True)
+    # usage: time_sparse.py [C3 items in flight = 8] [which = c3,c4]
+    which = sys.argv[2] if len(sys.argv) > 2 else "c3,c4"
+    if "c3" in which:
+        run("C3 sparse BGP", 10000, 1, 30, int(sys.argv[1]) if len(sys.argv) > 1 else 8, False)
+    if "c4" in which:
+        run("C4 MBGP", 500, 100, 180, 4, True)
