@@ -159,20 +159,33 @@ __device__ __forceinline__ void slab_mm(const double* __restrict__ A, const doub
         for (int t = 0; t < 4; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
         const int k0 = (TRI == 2) ? rt * 8 : 0;
         const int k1 = (TRI == 1) ? min(Mz, rt * 8 + 8) : Mz;
-        // the A fragments come from global memory (L2): two k steps are kept in flight ahead of the MMAs
-        double an0 = (vm && k0 + c < Mz) ? pa[k0] : 0.0;
-        double an1 = (vm && k0 + 4 + c < Mz) ? pa[k0 + 4] : 0.0;
-        for (int k = k0; k < k1; k += 4) {
-            const double a = an0;
-            an0 = an1;
-            an1 = (vm && k + 8 + c < Mz) ? pa[k + 8] : 0.0;
-            const int kk = k + c;
-            const bool vk = kk < Mz;
-            const double* bk = Bs + (size_t)min(kk, Mz - 1) * SP_LDS + g;
+        // the A fragments come from global memory (L2, ~600 cycles): a block of 8 k steps (32 MMAs) is loaded while the previous
+        // block is multiplied
+        constexpr int PF = 8;
+        double nxt[PF];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const double b = vk ? bk[8 * t] : 0.0;
-                dmma(acc[t][0], acc[t][1], a, b);
+        for (int q = 0; q < PF; ++q) nxt[q] = (vm && k0 + 4 * q + c < Mz) ? pa[k0 + 4 * q] : 0.0;
+        for (int kb = k0; kb < k1; kb += 4 * PF) {
+            double cur[PF];
+#pragma unroll
+            for (int q = 0; q < PF; ++q) cur[q] = nxt[q];
+            if (kb + 4 * PF < k1) {
+#pragma unroll
+                for (int q = 0; q < PF; ++q) nxt[q] = (vm && kb + 4 * PF + 4 * q + c < Mz) ? pa[kb + 4 * PF + 4 * q] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int k = kb + 4 * q;
+                if (k < k1) {
+                    const int kk = k + c;
+                    const bool vk = kk < Mz;
+                    const double* bk = Bs + (size_t)min(kk, Mz - 1) * SP_LDS + g;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const double b = vk ? bk[8 * t] : 0.0;
+                        dmma(acc[t][0], acc[t][1], cur[q], b);
+                    }
+                }
             }
         }
         if (vm) {
@@ -189,11 +202,9 @@ __device__ __forceinline__ void slab_outer_lower(const double* __restrict__ As, 
     const int g = lane >> 2, c = lane & 3;
     const int nt = (Mz + 7) >> 3;
     const int ntiles = nt * (nt + 1) / 2;
-    for (int tix = warp; tix < ntiles; tix += SP_WARPS) {
-        int rt = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
-        while (rt * (rt + 1) / 2 > tix) --rt;
-        while ((rt + 1) * (rt + 2) / 2 <= tix) ++rt;
-        const int ct = tix - rt * (rt + 1) / 2;
+    int rt = 0, ct = warp;   // tile (rt, ct) of the lower triangle, advanced by SP_WARPS tiles per trip
+    for (int tix = warp; tix < ntiles; tix += SP_WARPS, ct += SP_WARPS) {
+        while (ct > rt) { ct -= rt + 1; ++rt; }
         const int m = rt * 8 + g, nr = ct * 8 + g;
         const bool vm = m < Mz, vn = nr < Mz;
         const double* pa = As + (size_t)min(m, Mz - 1) * SP_LDS + c;
@@ -279,6 +290,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
         // per-row / per-cell kernels against the branching point
         {
             const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
+#pragma unroll 4
             for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
                 const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
                 const int cell = j / 3, f = j - 3 * cell;
@@ -481,6 +493,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         __syncthreads();
         // hyper-gradient through K(Z, X): cross-function entries (products), then the same-function entry of every (row, cell) pair
         if (!empty) {
+#pragma unroll 4
             for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
                 const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
                 if (j >= M) continue;
@@ -519,52 +532,102 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------- k_sp_end
+// C = op(A) B on Mz x Mz row-major matrices in global memory (L2 resident) with the fp64 tensor pipe.  A warp owns an 8 x 32 strip
+// of C (four accumulator tiles); fragments are plain 8-byte loads, one k step ahead of the MMAs, and the kernel runs 32 warps so
+// that the L2 latency of the other warps' loads is covered.  KR selects the k range from the triangular structure of the operands:
+//   0:  T = Phi(L^T Lbar)   A = L read transposed, k >= m;  output columns n <= m, diagonal halved, zeros right of it
+//   1:  W = T Linv          n <= k <= m;  output tiles on / below the diagonal (entries right of the diagonal come out as 0)
+//   2:  S = Linv^T W        A = LinvT,  k >= max(m, n);  all tiles
+template <int KR>
+__device__ __forceinline__ void gmm_tri(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int Mz) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int nrt = (Mz + 7) >> 3, nst = (Mz + 31) >> 5;
+    for (int u = warp; u < nrt * nst; u += nwarps) {
+        const int rt = u / nst, stp = u - rt * nst;
+        const int m0 = rt * 8, n0 = stp * 32;
+        if (KR != 2 && n0 > m0 + 7) continue;
+        const int k0 = (KR == 0) ? m0 : (KR == 1 ? n0 : max(m0, n0));
+        const int k1 = (KR == 1) ? min(Mz, m0 + 8) : Mz;
+        const int m = m0 + g;
+        const bool vm = m < Mz;
+        double acc[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        auto lda = [&](int k) -> double {
+            const int kk = k + c;
+            if (!vm || kk >= Mz) return 0.0;
+            return (KR == 0) ? A[(size_t)kk * Mz + m] : A[(size_t)m * Mz + kk];
+        };
+        auto ldb = [&](int k, int t) -> double {
+            const int kk = k + c, n = n0 + 8 * t + g;
+            return (kk < Mz && n < Mz) ? B[(size_t)kk * Mz + n] : 0.0;
+        };
+        double an = lda(k0), bn[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bn[t] = ldb(k0, t);
+        for (int k = k0; k < k1; k += 4) {
+            const double a = an;
+            double b[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) b[t] = bn[t];
+            if (k + 4 < k1) {
+                an = lda(k + 4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) bn[t] = ldb(k + 4, t);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dmma(acc[t][0], acc[t][1], a, b[t]);
+        }
+        if (vm) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int n = n0 + 8 * t + 2 * c + q;
+                    if (n >= Mz) continue;
+                    double v = acc[t][q];
+                    if (KR == 0) v = (n > m) ? 0.0 : (n == m ? 0.5 * v : v);
+                    C[(size_t)m * Mz + n] = v;
+                }
+        }
+    }
+}
+
 // Cholesky adjoint of Kuu (Kuu_bar = sym(Linv^T Phi(L^T Lbar) Linv)), hyper-gradient through K(Z,Z), assembly of the
 // sub-problem's bound and gradient.  outputs: sub_out[slot][8] = elbo, g_ell, g_var, g_lik, g_b
-__global__ void __launch_bounds__(NTHREADS) k_sp_end(SparseParams P, double* sub_out) {
+constexpr int SP_END_THREADS = 512;
+__global__ void __launch_bounds__(SP_END_THREADS) k_sp_end(SparseParams P, double* sub_out) {
     SP_SETUP();
     __shared__ double red[32];
+    const int NT = blockDim.x;
     const double* L = ws + SLy.L;
     const double* Linv = ws + SLy.Linv;
+    const double* LinvT = ws + SLy.LinvT;
     double* T = ws + SLy.T;
     double* W = ws + SLy.W;
     double* S = ws + SLy.S;
     double gl = 0.0, gv = 0.0, gb = 0.0;
     if (P.want_grad) {
-    // T = Phi(L^T Lbar): T[m][n] = sum_{k >= m} L[k][m] Lbar[k][n],  n <= m, diagonal halved
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
-        const int m = e / Mz, n = e % Mz;
-        double s = 0.0;
-        if (n <= m) {
-            for (int k = m; k < Mz; ++k) {
-                double lb = 0.0;
-                for (int sp = 0; sp < P.nsplit; ++sp) lb += ws[SLy.Lbpart + (size_t)sp * Mz * Mz + (size_t)k * Mz + n];
-                s += L[(size_t)k * Mz + m] * lb;
-            }
-            if (n == m) s *= 0.5;
+    // Lbar = sum of the column splits' partials (lower triangle; what lies above it is never part of a result)
+    double* Lb = ws + SLy.Lbpart;
+    if (P.nsplit > 1) {
+        for (int e = tid; e < Mz * Mz; e += NT) {
+            if (e % Mz > e / Mz) continue;
+            double lb = Lb[e];
+            for (int sp = 1; sp < P.nsplit; ++sp) lb += Lb[(size_t)sp * Mz * Mz + e];
+            Lb[e] = lb;
         }
-        T[e] = s;
+        __syncthreads();
     }
+    gmm_tri<0>(L, Lb, T, Mz);        // T = Phi(L^T Lbar)
     __syncthreads();
-    // W = T Linv  (lower): W[m][n] = sum_{n <= k <= m} T[m][k] Linv[k][n]
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
-        const int m = e / Mz, n = e % Mz;
-        double s = 0.0;
-        if (n <= m)
-            for (int k = n; k <= m; ++k) s += T[(size_t)m * Mz + k] * Linv[(size_t)k * Mz + n];
-        W[e] = s;
-    }
+    gmm_tri<1>(T, Linv, W, Mz);      // W = T Linv
     __syncthreads();
-    // S = Linv^T W: S[m][n] = sum_{k >= max(m,n)} Linv[k][m] W[k][n]
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
-        const int m = e / Mz, n = e % Mz;
-        double s = 0.0;
-        for (int k = (m > n ? m : n); k < Mz; ++k) s += Linv[(size_t)k * Mz + m] * W[(size_t)k * Mz + n];
-        S[e] = s;
-    }
+    gmm_tri<2>(LinvT, W, S, Mz);     // S = Linv^T W
     __syncthreads();
     // hyper-gradient through K(Z,Z): Kuu_bar = (S + S^T)/2, full sum
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    for (int e = tid; e < Mz * Mz; e += NT) {
         const int m = e / Mz, n = e % Mz;
         const double w = 0.5 * (S[e] + S[(size_t)n * Mz + m]);
         const int fm = (int)P.Z[2 * m + 1], fn = (int)P.Z[2 * n + 1];
@@ -716,7 +779,7 @@ void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* s
         case 3: k_sp_mid<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
         case 4: k_sp_bwd<<<gs, NTHREADS, slab_bytes(P.Mz, 3), st>>>(P); break;
         case 5: {
-            k_sp_end<<<g1, NTHREADS, 0, st>>>(P, sub_out);
+            k_sp_end<<<g1, SP_END_THREADS, 0, st>>>(P, sub_out);
             const int nitems = nslots / P.SD;
             k_sp_reduce<<<(nitems + 127) / 128, 128, 0, st>>>(P, sub_out, nitems);
             break;

@@ -70,9 +70,21 @@ def run(name, N, Dtot, Mz, count, multi, reps=3):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
+    # roofline figures of SURVEY.md 8(d): algorithmic bytes = logPhi read + gradient write (2 x 8 x 3N^2 per item); algorithmic flops
+    # of the inducing-point algebra = D (4 Mz^2 3N + Mz^3) per item.  Peaks: MEASURED_PEAKS.json (HBM copy), profiles/r01_fp64_peak.json.
     bytes_alg = 2.0 * 8 * N * M * count
+    flops_alg = float(Dtot) * (4.0 * Mz * Mz * M + float(Mz) ** 3) * count
+    hbm_peak, dmma_peak = 6545.6, 37.14
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    gbps = bytes_alg / best / 1e6
+    tflops = flops_alg / best / 1e9
     print(json.dumps({"config": name, "N": N, "D": Dtot, "Mz": Mz, "items": count, "ms": round(best, 3),
-                      "items_per_s": round(count / best * 1e3, 2), "logPhi_GBps": round(bytes_alg / best / 1e6, 1),
+                      "items_per_s": round(count / best * 1e3, 2), "logPhi_GBps": round(gbps, 1),
+                      "frac_hbm_peak_algorithmic": round(gbps / hbm_peak, 4), "algebra_TFLOPs": round(tflops, 3),
+                      "frac_dmma_peak": round(tflops / dmma_peak, 4),
                       "status_nonzero": int((st != 0).sum().item()), "elbo0": float(elbo[0].item())}))
 
 
