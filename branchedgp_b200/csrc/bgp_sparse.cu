@@ -137,7 +137,11 @@ __device__ __forceinline__ double kuf_entry(const SparseParams& P, const double*
 // columns of X; SP_LDS = 36 makes both fragment patterns below bank-conflict free: 36 = 4 mod 16 eight-byte banks).
 // lane = 4 g + c:  a = A[g][c],  b = B[c][g],  d = {D[g][2c], D[g][2c + 1]}.
 constexpr int SP_LDS = SP_SL + 4;
-constexpr int SP_WARPS = NTHREADS / 32;
+#ifndef BGP_SP_T
+#define BGP_SP_T 512
+#endif
+constexpr int SP_T = BGP_SP_T;             // threads of the slab kernels (k_sp_fwd, k_sp_bwd)
+constexpr int SP_WARPS = SP_T / 32;
 
 // Cs[m][0..32) = sum_k A[m][k] Bs[k][.],  A = Mz x Mz row-major in global memory (L1 / L2 resident, explicit zeros outside its
 // triangle).  TRI: 0 full, 1 lower (k <= m), 2 upper (k >= m) -- only narrows the k range.
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_kuu(SparseParams P) {
 
 // ---------------------------------------------------------------------------------------------------- k_sp_fwd
 // grid (nsplit, slots).  V = Linv Kuf for this CTA's slabs; partial P = V Delta V^T, z = V v, trace.
-__global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
+__global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
     SP_SETUP();
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
         {
             const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
 #pragma unroll 4
-            for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            for (int e = tid; e < Mz * SP_SL; e += SP_T) {
                 const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
                 const int cell = j / 3, f = j - 3 * cell;
                 const int fz = (int)P.Z[2 * m + 1] - 1;
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
                 else if (fz != f) Ks[m * LDS_ + jj] = (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
             }
             if (!empty)
-                for (int e = tid; e < Mz * ncell; e += NTHREADS) {
+                for (int e = tid; e < Mz * ncell; e += SP_T) {
                     const int m = e / ncell, cell = cell0 + e % ncell;
                     const int jj = 3 * cell + (int)P.Z[2 * m + 1] - 1 - j0;
                     if (jj >= 0 && jj < SP_SL && j0 + jj < M) Ks[m * LDS_ + jj] = kbase(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind);
@@ -309,20 +313,20 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_fwd(SparseParams P) {
         __syncthreads();
         slab_mm<1>(Linv, Ks, Vs, Mz, warp, lane);   // V = Linv K(Z, X_slab)
         __syncthreads();
-        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+        for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL;
             const double x = Vs[m * LDS_ + jj];
             if (!empty && j0 + jj < Mp) ws[SLy.V + (size_t)m * Mp + j0 + jj] = x;
             tr += Dls[jj] * x * x;
         }
         // Ks <- Delta_j V (scaled copy) so that P += Ks Vs^T
-        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+        for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL;
             Ks[m * LDS_ + jj] = Dls[jj] * Vs[m * LDS_ + jj];
         }
         __syncthreads();
         slab_outer_lower(Ks, Vs, Pp, Mz, first, 1.0, warp, lane);
-        for (int e = tid; e < D * Mz; e += NTHREADS) {
+        for (int e = tid; e < D * Mz; e += SP_T) {
             const int d = e / Mz, m = e % Mz;
             double s = 0.0;
             if (!empty)
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
 
 // ---------------------------------------------------------------------------------------------------- k_sp_bwd
 // grid (nsplit, slots).  Per slab: U = Pbar V, delta, Abar, vbar, Vbar, Kuf_bar = Linv^T Vbar, partial Lbar, hyper-gradient of Kuf.
-__global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
+__global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
     SP_SETUP();
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         const bool empty = sl >= nslab;
         const int j0 = sl * SP_SL;
         __syncthreads();
-        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+        for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
             Vs[m * LDS_ + jj] = (!empty && j < M) ? ws[SLy.V + (size_t)m * Mp + j] : 0.0;
         }
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
             __syncthreads();
         }
         // Vbar = 2 Delta U + zbar v^T + Delta V
-        for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+        for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
             double zv = 0.0;
             if (!empty && j < M)
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
         // hyper-gradient through K(Z, X): cross-function entries (products), then the same-function entry of every (row, cell) pair
         if (!empty) {
 #pragma unroll 4
-            for (int e = tid; e < Mz * SP_SL; e += NTHREADS) {
+            for (int e = tid; e < Mz * SP_SL; e += SP_T) {
                 const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
                 if (j >= M) continue;
                 const int cell = j / 3, f = j - 3 * cell;
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_bwd(SparseParams P) {
                 gb += w * (ws[SLy.dkabz + m] * b + a * ws[SLy.dkabx + cell]) * kinv;
             }
             const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
-            for (int e = tid; e < Mz * ncell; e += NTHREADS) {
+            for (int e = tid; e < Mz * ncell; e += SP_T) {
                 const int m = e / ncell, cell = cell0 + e % ncell;
                 const int jj = 3 * cell + (int)P.Z[2 * m + 1] - 1 - j0;
                 if (jj < 0 || jj >= SP_SL || j0 + jj >= M) continue;
@@ -775,9 +779,9 @@ void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* s
             k_sp_prep<<<g1, NTHREADS, 0, st>>>(P);
             break;
         case 1: k_sp_kuu<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
-        case 2: k_sp_fwd<<<gs, NTHREADS, slab_bytes(P.Mz, 2), st>>>(P); break;
+        case 2: k_sp_fwd<<<gs, SP_T, slab_bytes(P.Mz, 2), st>>>(P); break;
         case 3: k_sp_mid<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
-        case 4: k_sp_bwd<<<gs, NTHREADS, slab_bytes(P.Mz, 3), st>>>(P); break;
+        case 4: k_sp_bwd<<<gs, SP_T, slab_bytes(P.Mz, 3), st>>>(P); break;
         case 5: {
             k_sp_end<<<g1, SP_END_THREADS, 0, st>>>(P, sub_out);
             const int nitems = nslots / P.SD;
