@@ -68,6 +68,145 @@ __device__ void trinv_packed(double* A, int n) {
     }
 }
 
+// ---- blocked versions on the fp64 tensor pipe (8 x 8 blocks = one DMMA tile; the packed layout is addressed element by element,
+// which is all a DMMA fragment needs).  `dinv` receives the inverses of the diagonal blocks ([blocks][64], zero above the
+// diagonal and in the padding of a ragged last block); the inverse routine reuses them.
+__device__ __forceinline__ int pk_blocks(int n) { return (n + 7) >> 3; }
+
+// Right-looking: diagonal block factored + inverted by warp 0, panel = A_panel inv(L_JJ)^T with a thread per row, trailing
+// lower tiles updated by rank-8 MMAs.  Three CTA barriers per 8 columns instead of three per column.
+__device__ void chol_packed_blocked(double* A, int n, int& fail, double* dinv) {
+    __shared__ int fail_s;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int nblk = pk_blocks(n);
+    if (tid == 0) fail_s = 0;
+    for (int J = 0; J < nblk; ++J) {
+        const int j0 = 8 * J, w = min(8, n - j0);
+        double* Dv = dinv + 64 * J;
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = 0; j < w; ++j) {   // lane = row of the block, left-looking inside the block
+                double a = 0.0;
+                if (lane < w && lane >= j) {
+                    a = A[pk(j0 + lane, j0 + j)];
+                    for (int k = 0; k < j; ++k) a -= A[pk(j0 + lane, j0 + k)] * A[pk(j0 + j, j0 + k)];
+                }
+                double d = __shfl_sync(0xffffffffu, a, j);
+                if (!(d > 0.0)) {
+                    if (lane == 0 && fail_s == 0) fail_s = j0 + j + 1;
+                    d = 1.0;
+                }
+                const double r = sqrt(d);
+                __syncwarp();
+                if (lane < w && lane >= j) A[pk(j0 + lane, j0 + j)] = (lane == j) ? r : a / r;
+                __syncwarp();
+            }
+            for (int e = lane; e < 64; e += 32) Dv[e] = 0.0;
+            __syncwarp();
+            if (lane < w) {   // lane = column of the inverse, forward substitution
+                for (int i = lane; i < w; ++i) {
+                    double sacc = (i == lane) ? 1.0 : 0.0;
+                    for (int k = lane; k < i; ++k) sacc -= A[pk(j0 + i, j0 + k)] * Dv[k * 8 + lane];
+                    Dv[i * 8 + lane] = sacc / A[pk(j0 + i, j0 + i)];
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = j0 + w + tid; i < n; i += nt) {   // panel row i:  L_i = A_i inv(L_JJ)^T
+            double a[8], l[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = (k < w) ? A[pk(i, j0 + k)] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k <= cc; ++k) sacc = fma(a[k], Dv[cc * 8 + k], sacc);
+                l[cc] = sacc;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+                if (cc < w) A[pk(i, j0 + cc)] = l[cc];
+        }
+        __syncthreads();
+        const int T0 = J + 1, nrem = nblk - T0;   // trailing tiles (rt, ct), T0 <= ct <= rt < nblk
+        int rr = 0, cr = warp;
+        for (int tix = warp; tix < nrem * (nrem + 1) / 2; tix += nwarps, cr += nwarps) {
+            while (cr > rr) { cr -= rr + 1; ++rr; }
+            const int m = 8 * (T0 + rr) + g, nrow = 8 * (T0 + cr) + g, n0 = 8 * (T0 + cr) + 2 * c;
+            const bool vm = m < n;
+            double d0 = (vm && n0 <= m) ? A[pk(m, n0)] : 0.0;
+            double d1 = (vm && n0 + 1 <= m) ? A[pk(m, n0 + 1)] : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4) {
+                const bool vk = kk + c < w;
+                const double a = (vm && vk) ? -A[pk(m, j0 + kk + c)] : 0.0;
+                const double b = (nrow < n && vk) ? A[pk(nrow, j0 + kk + c)] : 0.0;
+                dmma(d0, d1, a, b);
+            }
+            if (vm && n0 <= m) A[pk(m, n0)] = d0;
+            if (vm && n0 + 1 <= m) A[pk(m, n0 + 1)] = d1;
+        }
+    }
+    __syncthreads();
+    if (fail == 0) fail = fail_s;
+    __syncthreads();
+}
+
+// In-place inverse of the packed lower-triangular factor, one 8-row block at a time:  X_IJ = -inv(L_II) sum_{J <= K < I} L_IK X_KJ.
+// Row block I of L is read by every warp before any of it is overwritten (results wait in registers across the barrier).
+// `wscr`: 8 x 9 doubles per warp.  Needs (blocks - 1) <= 4 x warps.
+__device__ void trinv_packed_blocked(double* A, int n, const double* dinv, double* wscr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int nblk = pk_blocks(n);
+    double* S = wscr + warp * 72;
+    for (int I = 0; I < nblk; ++I) {
+        const int i0 = 8 * I;
+        const double* Dv = dinv + 64 * I;
+        const int m = i0 + g;
+        const bool vm = m < n;
+        double res[4][2];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int J = warp + q * nwarps;
+            res[q][0] = 0.0; res[q][1] = 0.0;
+            if (J < I) {
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                const int bcol = 8 * J + g;
+                for (int K = J; K < I; ++K) {
+                    const int r0 = 8 * K + c, r1 = r0 + 4;
+                    const double a0 = vm ? A[pk(m, r0)] : 0.0, a1 = vm ? A[pk(m, r1)] : 0.0;
+                    const double b0 = (bcol <= r0) ? A[pk(r0, bcol)] : 0.0, b1 = (bcol <= r1) ? A[pk(r1, bcol)] : 0.0;
+                    dmma(d0, d1, a0, b0);
+                    dmma(e0, e1, a1, b1);
+                }
+                S[g * 9 + 2 * c] = d0 + e0;
+                S[g * 9 + 2 * c + 1] = d1 + e1;
+                __syncwarp();
+                double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk += 4) dmma(x0, x1, -Dv[g * 8 + kk + c], S[(kk + c) * 9 + g]);
+                res[q][0] = x0; res[q][1] = x1;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int J = warp + q * nwarps;
+            if (J < I && vm) { A[pk(m, 8 * J + 2 * c)] = res[q][0]; A[pk(m, 8 * J + 2 * c + 1)] = res[q][1]; }
+        }
+        if (warp == nwarps - 1)
+            for (int e = lane; e < 64; e += 32) {
+                const int r = e >> 3, cc = e & 7;
+                if (cc <= r && i0 + r < n) A[pk(i0 + r, i0 + cc)] = Dv[e];
+            }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------- k_sp_reduce_partials
 // A_j, Delta_j, v_jd from the row-chunk partials of the assignment pass; grid (column blocks, slots) so that the
 // nch x Mp partial arrays (300 MB per item at N = 10 000) are read with the whole GPU, in a fixed order (deterministic).
@@ -140,7 +279,7 @@ constexpr int SP_LDS = SP_SL + 4;
 #ifndef BGP_SP_T
 #define BGP_SP_T 512
 #endif
-constexpr int SP_T = BGP_SP_T;             // threads of the slab kernels (k_sp_fwd, k_sp_bwd)
+constexpr int SP_T = BGP_SP_T;             // threads of the slab kernels (k_sp_fwd, k_sp_bwd) and of k_sp_kuu / k_sp_mid
 constexpr int SP_WARPS = SP_T / 32;
 
 // Cs[m][0..32) = sum_k A[m][k] Bs[k][.],  A = Mz x Mz row-major in global memory (L1 / L2 resident, explicit zeros outside its
@@ -239,11 +378,11 @@ __device__ __forceinline__ void slab_outer_lower(const double* __restrict__ As, 
 }
 
 // ---------------------------------------------------------------------------------------------------- k_sp_kuu
-__global__ void __launch_bounds__(NTHREADS) k_sp_kuu(SparseParams P) {
+__global__ void __launch_bounds__(SP_T) k_sp_kuu(SparseParams P) {
     SP_SETUP();
     extern __shared__ __align__(16) double sm[];
     int fail = 0;
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         if (n > m) continue;
         const int fm = (int)P.Z[2 * m + 1], fn = (int)P.Z[2 * n + 1];
@@ -252,14 +391,16 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_kuu(SparseParams P) {
         sm[pk(m, n)] = k;
     }
     __syncthreads();
-    chol_packed(sm, Mz, fail);
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    double* const dinv = sm + (size_t)Mz * (Mz + 1) / 2;          // inverse diagonal blocks, then per-warp scratch
+    double* const wscr = dinv + 64 * pk_blocks(Mz);
+    chol_packed_blocked(sm, Mz, fail, dinv);
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         ws[SLy.L + e] = (n <= m) ? sm[pk(m, n)] : 0.0;
     }
     __syncthreads();
-    trinv_packed(sm, Mz);
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    trinv_packed_blocked(sm, Mz, dinv, wscr);
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         const double x = (n <= m) ? sm[pk(m, n)] : 0.0;
         ws[SLy.Linv + e] = x;
@@ -341,12 +482,12 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------- k_sp_mid
-__global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
+__global__ void __launch_bounds__(SP_T) k_sp_mid(SparseParams P) {
     SP_SETUP();
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     int fail = 0;
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         if (n > m) continue;
         double s = (m == n) ? 1.0 : 0.0;
@@ -354,17 +495,19 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
         sm[pk(m, n)] = s;
     }
     __syncthreads();
-    chol_packed(sm, Mz, fail);
+    double* const dinv = sm + (size_t)Mz * (Mz + 1) / 2;          // inverse diagonal blocks, then per-warp scratch
+    double* const wscr = dinv + 64 * pk_blocks(Mz);
+    chol_packed_blocked(sm, Mz, fail, dinv);
     double ld = 0.0;
-    for (int m = tid; m < Mz; m += NTHREADS) { const double r = sm[pk(m, m)]; ld += log(r * r); }
+    for (int m = tid; m < Mz; m += SP_T) { const double r = sm[pk(m, m)]; ld += log(r * r); }
     ld = block_sum(ld, red);
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         ws[SLy.R + e] = (n <= m) ? sm[pk(m, n)] : 0.0;
     }
     __syncthreads();
-    trinv_packed(sm, Mz);   // sm = R^-1 (packed)
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    trinv_packed_blocked(sm, Mz, dinv, wscr);   // sm = R^-1 (packed)
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         ws[SLy.Rinv + e] = (n <= m) ? sm[pk(m, n)] : 0.0;
     }
@@ -375,13 +518,13 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
         double* cv = ws + SLy.c + (size_t)d * Mz;
         double* q = ws + SLy.q + (size_t)d * Mz;
         double* zb = ws + SLy.zbar + (size_t)d * Mz;
-        for (int m = tid; m < Mz; m += NTHREADS) {
+        for (int m = tid; m < Mz; m += SP_T) {
             double s = 0.0;
             for (int sp = 0; sp < P.nsplit; ++sp) s += ws[SLy.zpart + ((size_t)sp * D + d) * Mz + m];
             z[m] = s;
         }
         __syncthreads();
-        for (int m = tid; m < Mz; m += NTHREADS) {
+        for (int m = tid; m < Mz; m += SP_T) {
             double s = 0.0;
             for (int k = 0; k <= m; ++k) s += sm[pk(m, k)] * z[k];
             s /= likvar;
@@ -389,7 +532,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
             c2 += s * s;
         }
         __syncthreads();
-        for (int m = tid; m < Mz; m += NTHREADS) {
+        for (int m = tid; m < Mz; m += SP_T) {
             double s = 0.0;
             for (int k = m; k < Mz; ++k) s += sm[pk(k, m)] * cv[k];
             q[m] = s;
@@ -400,7 +543,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_mid(SparseParams P) {
     c2 = block_sum(c2, red);
     // Pbar = -D/2 R^-T R^-1 - 1/2 q q^T   (full symmetric)
     const double hD = 0.5 * (double)D;
-    for (int e = tid; e < Mz * Mz; e += NTHREADS) {
+    for (int e = tid; e < Mz * Mz; e += SP_T) {
         const int m = e / Mz, n = e % Mz;
         if (n > m) continue;
         double s = 0.0;
@@ -757,7 +900,9 @@ void sparse_launch_predict(const SparseParams& P, const double* Xnew, int T, int
 }
 
 // ---------------------------------------------------------------------------------------------------- launchers
-static size_t packed_bytes(int Mz) { return (size_t)Mz * (Mz + 1) / 2 * 8; }
+static size_t packed_bytes(int Mz) {   // packed lower triangle + inverse diagonal blocks + 8 x 9 scratch per warp
+    return ((size_t)Mz * (Mz + 1) / 2 + 64 * (size_t)((Mz + 7) / 8) + 72 * (SP_T / 32)) * 8;
+}
 static size_t slab_bytes(int Mz, int nbuf) { return ((size_t)nbuf * Mz * SP_LDS + SP_SL) * 8; }
 
 cudaError_t sparse_init_kernels() {
@@ -778,9 +923,9 @@ void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* s
             k_sp_reduce_partials<<<dim3((P.Mp + NTHREADS - 1) / NTHREADS, nslots), NTHREADS, 0, st>>>(P);
             k_sp_prep<<<g1, NTHREADS, 0, st>>>(P);
             break;
-        case 1: k_sp_kuu<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
+        case 1: k_sp_kuu<<<g1, SP_T, packed_bytes(P.Mz), st>>>(P); break;
         case 2: k_sp_fwd<<<gs, SP_T, slab_bytes(P.Mz, 2), st>>>(P); break;
-        case 3: k_sp_mid<<<g1, NTHREADS, packed_bytes(P.Mz), st>>>(P); break;
+        case 3: k_sp_mid<<<g1, SP_T, packed_bytes(P.Mz), st>>>(P); break;
         case 4: k_sp_bwd<<<gs, SP_T, slab_bytes(P.Mz, 3), st>>>(P); break;
         case 5: {
             k_sp_end<<<g1, SP_END_THREADS, 0, st>>>(P, sub_out);
