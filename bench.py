@@ -320,6 +320,25 @@ def run_ours(args):
                "evals_per_s": round(float(nev.item()) / float(tf.item()), 2), "status_counts": np.bincount(fo["status"], minlength=6).tolist(),
                "note": "wall clock of the whole call incl. allocation of the optimiser state and the final Phi / prediction outputs"}
 
+    # ---- the inducing-point configurations of BASELINE.json (C3 sparse BGP, C4 MBGP), device-resident inputs, N = 1 only:
+    # parity-test cases, reported beside the headline so that their roofline figures come from the same run
+    other = None
+    if world == 1 and not args.no_sparse:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import time_sparse
+            del keep
+            eng.close()                 # gives back the dense workspace and the optimiser state of the fit (116 GB)
+            torch.cuda.empty_cache()
+            eng = _lib.Engine(local)
+            other = {"note": "bound + gradient evaluations/s with inputs resident in HBM (tools/time_sparse.py); C3: HBM bound, fraction = "
+                             "algorithmic logPhi + gradient bytes (16 B per element) over the measured copy bandwidth; C4: algebra flops "
+                             "D (4 Mz^2 3N + Mz^3) over the measured DMMA peak",
+                     "C3": time_sparse.run("C3 sparse BGP: N=10000, Mz=30", 10000, 1, 30, 8, False, eng=eng, verbose=False),
+                     "C4": time_sparse.run("C4 MBGP: N=500, D=100, Mz=180", 500, 100, 180, 4, True, eng=eng, verbose=False)}
+        except Exception as exc:   # never lose the headline line to a side measurement
+            other = {"error": repr(exc)}
+
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -327,7 +346,7 @@ def run_ours(args):
                        "items_per_step_per_gpu": ips, "cells": N, "D": 1, "kernel": "Matern32",
                        "l2": "inputs larger than L2 (logPhi+grad = %.1f GB per step), no flush" % (2 * ips * N * 3 * N * 8 / 1e9),
                        "parallelism": f"items sharded over {world} GPU(s), NCCL all_gather of [items,5] results per step"},
-            "e2e": e2e, "fit": fit, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "status_nonzero": bad}
+            "e2e": e2e, "fit": fit, "other_configs": other, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "status_nonzero": bad}
     if rank == 0 and world == 1 and not args.no_cpu:   # reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(N, H, kind="port", budget_s=args.cpu_seconds)
     if rank == 0:
@@ -454,6 +473,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the C3 / C4 side measurements")
     ap.add_argument("--fit-items", type=int, default=148)
     ap.add_argument("--fit-maxiter", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")

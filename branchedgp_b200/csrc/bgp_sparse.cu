@@ -86,29 +86,38 @@ __device__ void chol_packed_blocked(double* A, int n, int& fail, double* dinv) {
         double* Dv = dinv + 64 * J;
         __syncthreads();
         if (warp == 0) {
-            for (int j = 0; j < w; ++j) {   // lane = row of the block, left-looking inside the block
-                double a = 0.0;
-                if (lane < w && lane >= j) {
-                    a = A[pk(j0 + lane, j0 + j)];
-                    for (int k = 0; k < j; ++k) a -= A[pk(j0 + lane, j0 + k)] * A[pk(j0 + j, j0 + k)];
-                }
-                double d = __shfl_sync(0xffffffffu, a, j);
+            // the 8 x 8 diagonal block in the registers of lanes 0..7 (lane = row; rows beyond a ragged edge are identity rows):
+            // pivots and multipliers travel by shuffles, no shared-memory round trip on the critical path of the whole CTA
+            double a[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = (lane < w && k <= lane) ? A[pk(j0 + lane, j0 + k)] : ((k == lane) ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double sacc = a[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) sacc = fma(-a[k], __shfl_sync(0xffffffffu, a[k], j), sacc);
+                double d = __shfl_sync(0xffffffffu, sacc, j);
                 if (!(d > 0.0)) {
                     if (lane == 0 && fail_s == 0) fail_s = j0 + j + 1;
                     d = 1.0;
                 }
                 const double r = sqrt(d);
-                __syncwarp();
-                if (lane < w && lane >= j) A[pk(j0 + lane, j0 + j)] = (lane == j) ? r : a / r;
-                __syncwarp();
+                a[j] = (lane < j) ? 0.0 : ((lane == j) ? r : sacc / r);
             }
-            for (int e = lane; e < 64; e += 32) Dv[e] = 0.0;
-            __syncwarp();
-            if (lane < w) {   // lane = column of the inverse, forward substitution
-                for (int i = lane; i < w; ++i) {
-                    double sacc = (i == lane) ? 1.0 : 0.0;
-                    for (int k = lane; k < i; ++k) sacc -= A[pk(j0 + i, j0 + k)] * Dv[k * 8 + lane];
-                    Dv[i * 8 + lane] = sacc / A[pk(j0 + i, j0 + i)];
+            double x[8];   // lane = column of the inverse
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) sacc = fma(-__shfl_sync(0xffffffffu, a[k], i), x[k], sacc);
+                const double lii = __shfl_sync(0xffffffffu, a[i], i);
+                x[i] = (i >= lane) ? sacc / lii : 0.0;
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (lane < w && k <= lane) A[pk(j0 + lane, j0 + k)] = a[k];
+                    Dv[k * 8 + lane] = (k < w && lane < w) ? x[k] : 0.0;
                 }
             }
         }
@@ -541,18 +550,36 @@ __global__ void __launch_bounds__(SP_T) k_sp_mid(SparseParams P) {
         __syncthreads();
     }
     c2 = block_sum(c2, red);
-    // Pbar = -D/2 R^-T R^-1 - 1/2 q q^T   (full symmetric)
-    const double hD = 0.5 * (double)D;
-    for (int e = tid; e < Mz * Mz; e += SP_T) {
-        const int m = e / Mz, n = e % Mz;
-        if (n > m) continue;
-        double s = 0.0;
-        for (int k = m; k < Mz; ++k) s += sm[pk(k, m)] * sm[pk(k, n)];
-        double qq = 0.0;
-        for (int d = 0; d < D; ++d) qq += ws[SLy.q + (size_t)d * Mz + m] * ws[SLy.q + (size_t)d * Mz + n];
-        const double pb = -hD * s - 0.5 * qq;
-        ws[SLy.Pbar + (size_t)m * Mz + n] = pb;
-        ws[SLy.Pbar + (size_t)n * Mz + m] = pb;
+    // Pbar = -D/2 R^-T R^-1 - 1/2 q q^T   (full symmetric): 8 x 8 tiles of the lower triangle, X = R^-1 read from the packed matrix
+    {
+        const double hD = 0.5 * (double)D;
+        const int g = lane >> 2, c = lane & 3;
+        const int nblk = pk_blocks(Mz);
+        int rt = 0, ct = warp;
+        for (int tix = warp; tix < nblk * (nblk + 1) / 2; tix += SP_WARPS, ct += SP_WARPS) {
+            while (ct > rt) { ct -= rt + 1; ++rt; }
+            const int ma = 8 * rt + g, nb = 8 * ct + g;   // columns of X feeding the A / B fragments
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            for (int K = rt; K < nblk; ++K) {
+                const int r0 = 8 * K + c, r1 = r0 + 4;
+                const double a0 = (r0 < Mz && ma <= r0) ? sm[pk(r0, ma)] : 0.0, a1 = (r1 < Mz && ma <= r1) ? sm[pk(r1, ma)] : 0.0;
+                const double b0 = (r0 < Mz && nb <= r0) ? sm[pk(r0, nb)] : 0.0, b1 = (r1 < Mz && nb <= r1) ? sm[pk(r1, nb)] : 0.0;
+                dmma(d0, d1, a0, b0);
+                dmma(e0, e1, a1, b1);
+            }
+            d0 += e0; d1 += e1;
+            const int m = 8 * rt + g;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int n = 8 * ct + 2 * c + q;
+                if (m >= Mz || n > m) continue;
+                double qq = 0.0;
+                for (int d = 0; d < D; ++d) qq += ws[SLy.q + (size_t)d * Mz + m] * ws[SLy.q + (size_t)d * Mz + n];
+                const double pb = -hD * (q ? d1 : d0) - 0.5 * qq;
+                ws[SLy.Pbar + (size_t)m * Mz + n] = pb;
+                ws[SLy.Pbar + (size_t)n * Mz + m] = pb;
+            }
+        }
     }
     if (tid == 0) {
         ws[SLy.scal + SS_LOGDET] = ld;

@@ -11,9 +11,11 @@ sys.path.insert(0, ROOT)
 from branchedgp_b200 import _lib  # noqa: E402
 
 
-def run(name, N, Dtot, Mz, count, multi, reps=3):
-    dev = torch.device("cuda:0")
-    eng = _lib.Engine(0)
+def run(name, N, Dtot, Mz, count, multi, reps=3, eng=None, verbose=True):
+    """Times `count` work items of one inducing-point configuration with device-resident inputs; returns the result line as a dict
+    (phases_ms = CUDA-event time per pipeline phase of one call)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    eng = eng if eng is not None else _lib.Engine(torch.cuda.current_device())
     lib, h = eng._lib, eng._h
     g = torch.Generator().manual_seed(0)
     M = 3 * N
@@ -61,7 +63,9 @@ def run(name, N, Dtot, Mz, count, multi, reps=3):
     eng.profile_enable(False)
     names = dict(phi_forward="phi_fwd", prep="prep", chol_K="kuu", syrk_P="fwd_slabs", chol_P="mid", solve="bwd_slabs", trtri="end",
                  phi_backward="phi_bwd")
-    print(json.dumps({names[k]: round(v, 3) for k, v in ph.items() if k in names}))
+    phases = {names[k]: round(v, 3) for k, v in ph.items() if k in names}
+    if verbose:
+        print(json.dumps(phases))
     best = 1e30
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,11 +85,15 @@ def run(name, N, Dtot, Mz, count, multi, reps=3):
         pass
     gbps = bytes_alg / best / 1e6
     tflops = flops_alg / best / 1e9
-    print(json.dumps({"config": name, "N": N, "D": Dtot, "Mz": Mz, "items": count, "ms": round(best, 3),
-                      "items_per_s": round(count / best * 1e3, 2), "logPhi_GBps": round(gbps, 1),
-                      "frac_hbm_peak_algorithmic": round(gbps / hbm_peak, 4), "algebra_TFLOPs": round(tflops, 3),
-                      "frac_dmma_peak": round(tflops / dmma_peak, 4),
-                      "status_nonzero": int((st != 0).sum().item()), "elbo0": float(elbo[0].item())}))
+    out = {"config": name, "N": N, "D": Dtot, "Mz": Mz, "items": count, "ms": round(best, 3),
+           "items_per_s": round(count / best * 1e3, 2), "logPhi_GBps": round(gbps, 1),
+           "frac_hbm_peak_algorithmic": round(gbps / hbm_peak, 4), "algebra_TFLOPs": round(tflops, 3),
+           "frac_dmma_peak": round(tflops / dmma_peak, 4),
+           "status_nonzero": int((st != 0).sum().item()), "elbo0": float(elbo[0].item())}
+    if verbose:
+        print(json.dumps(out))
+    out["phases_ms"] = phases
+    return out
 
 
 if __name__ == "__main__":
