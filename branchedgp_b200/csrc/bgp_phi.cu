@@ -133,6 +133,99 @@ __global__ void __launch_bounds__(NTHREADS) k_phi_forward(PhiParams P) {
     if (tid == 0) P.klpart[(size_t)slot * P.slot_stride + chunk] = kl;
 }
 
+
+// ------------------------------------------------------------------------------------------- MBGP multi-output forward pass
+// The outputs of the joint model share logPhi; only the trunk mask t_i > b_d differs (MBGP/assigngp.py:217-251).  The reference (and
+// k_phi_forward with one CTA column per sub-problem) redoes softmax, exp and log for every output; here a CTA (16 rows, one item)
+// does them once, keeps the 16 active-form values of its columns in registers and then only selects and accumulates per output:
+//   A_d[j] = sum_i (t_i > b_d ? Phi_ij : PhiTrunk_ij),  v_d[j] = sum_i (...) Y_id,  KL_d = sum_{i: t_i > b_d} KLrow_i
+// (a trunk row contributes exactly 0 to KL: its Phi and pZ are the same constant).  grid (row chunks, items), SD <= MO_MAXSD.
+constexpr int MO_MAXSD = 256;
+__global__ void __launch_bounds__(NTHREADS) k_phi_forward_multi(PhiParams P) {
+    __shared__ double lse_s[PHI_RCH], inv_dummy[1], t_s[PHI_RCH], klrow_s[PHI_RCH], red[32];
+    __shared__ double bv_s[MO_MAXSD];
+    __shared__ double Ys[PHI_RCH][MO_MAXSD];
+    (void)inv_dummy;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, litem = blockIdx.y, item = P.item0 + litem;
+    const int N = P.N, M = P.M, Mp = P.Mp, SD = P.SD;
+    const int r0 = chunk * PHI_RCH, nr = min(PHI_RCH, N - r0);
+    const size_t slot0 = (size_t)litem * SD;
+    const double* lp = P.logPhi + ((size_t)item * N + r0) * M;
+    double* stash = P.grad_logPhi ? P.grad_logPhi + ((size_t)item * N + r0) * M : nullptr;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* prior = P.prior;
+    for (int e = tid; e < PHI_RCH * SD; e += NTHREADS) {
+        const int rr = e / SD, sd = e - rr * SD;
+        Ys[rr][sd] = rr < nr ? Yg[(size_t)(r0 + rr) * P.Dtot + sd] : 0.0;
+    }
+    for (int sd = tid; sd < SD; sd += NTHREADS) bv_s[sd] = P.bv[(size_t)item * SD + sd];
+    if (tid < PHI_RCH) t_s[tid] = tid < nr ? P.t[r0 + tid] : -1.0e308;   // padding rows are trunk rows of every output ...
+    // ---- row log-sum-exp, one warp per row
+    for (int rr = warp; rr < nr; rr += NTHREADS / 32) {
+        const double* row = lp + (size_t)rr * M;
+        double m = -1.0e308;
+        for (int j = lane; j < M; j += 32) m = fmax(m, row[j]);
+        m = warp_max(m);
+        double sacc = 0.0;
+        for (int j = lane; j < M; j += 32) sacc += fast_exp(row[j] - m);
+        sacc = warp_sum(sacc);
+        const double l = m + log(sacc);
+        if (lane == 0) {
+            lse_s[rr] = l;
+            P.lse[slot0 * P.slot_stride + r0 + rr] = l;
+        }
+    }
+    __syncthreads();
+    const double lpz_off = log(SQ_A * 1e-6 + SQ_B);   // log pZ of every column outside the row's own cell (eZ0 = 1e-6 there)
+    double klr[PHI_RCH];
+#pragma unroll
+    for (int rr = 0; rr < PHI_RCH; ++rr) klr[rr] = 0.0;
+    for (int j = tid; j < Mp; j += NTHREADS) {
+        double pa[PHI_RCH], pt[PHI_RCH];   // active-form / trunk-form squashed probabilities of column j
+#pragma unroll
+        for (int rr = 0; rr < PHI_RCH; ++rr) {
+            pa[rr] = 0.0; pt[rr] = 0.0;    // ... and contribute nothing
+            if (rr < nr && j < M) {
+                const int row = r0 + rr;
+                const int f = j - 3 * row;
+                const bool inblock = (f >= 0 && f < 3);
+                const double S = fast_exp(lp[(size_t)rr * M + j] - lse_s[rr]);
+                if (stash) stash[(size_t)rr * M + j] = S;
+                const double phi = SQ_A * S + SQ_B;
+                pa[rr] = phi;
+                pt[rr] = SQ_A * trunk_value(inblock, f) + SQ_B;
+                const double lpz = inblock ? log_pz(MODEL_MBGP, true, true, f, prior, row, 0.0) : lpz_off;
+                klr[rr] += phi * (fast_log(phi) - lpz);
+            }
+        }
+        for (int sd = 0; sd < SD; ++sd) {
+            const double b = bv_s[sd];
+            double a = 0.0, v = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < PHI_RCH; ++rr) {
+                const double p = t_s[rr] > b ? pa[rr] : pt[rr];
+                a += p;
+                v = fma(p, Ys[rr][sd], v);
+            }
+            P.Apart[(slot0 + sd) * P.slot_stride + (size_t)chunk * Mp + j] = a;
+            P.vpart[(slot0 + sd) * P.slot_stride + (size_t)chunk * Mp + j] = v;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < PHI_RCH; ++rr) {
+        const double x = block_sum(klr[rr], red);
+        if (tid == 0) klrow_s[rr] = x;
+    }
+    __syncthreads();
+    for (int sd = tid; sd < SD; sd += NTHREADS) {
+        const double b = bv_s[sd];
+        double kl = 0.0;
+        for (int rr = 0; rr < nr; ++rr) kl += t_s[rr] > b ? klrow_s[rr] : 0.0;
+        P.klpart[(slot0 + sd) * P.slot_stride + chunk] = kl;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- row-resident forward
 // Bound + gradient calls with one sub-problem per item: the forward pass is split into a row pass and a column pass.
 //   k_phi_rowpass: one CTA (or a cluster of CL CTAs) owns one row of logPhi, which it reads ONCE into registers: max, e = exp(x - max),
@@ -974,6 +1067,11 @@ void phi_launch_forward(const PhiParams& P, int nsubs, cudaStream_t st) {
         else k_phi_rowpass<512, 12, 1, 1><<<dim3(P.N, nsubs), 512, 0, st>>>(P);
         if (P.D == 1) k_phi_colpass<1><<<grid, NTHREADS, 0, st>>>(P, 1);
         else k_phi_colpass<4><<<grid, NTHREADS, 0, st>>>(P, 1);
+        return;
+    }
+    const char* mo = getenv("BGP_PHI_MULTI");
+    if (P.SD > 1 && P.SD <= MO_MAXSD && P.D == 1 && P.model == MODEL_MBGP && nsubs % P.SD == 0 && !(mo && mo[0] == '0')) {
+        k_phi_forward_multi<<<dim3(P.nch, nsubs / P.SD), NTHREADS, 0, st>>>(P);   // shared softmax for the outputs of a joint model
         return;
     }
     if (P.D == 1) k_phi_forward<1><<<grid, NTHREADS, 0, st>>>(P);
