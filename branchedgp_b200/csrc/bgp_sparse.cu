@@ -285,6 +285,8 @@ __device__ __forceinline__ double kuf_entry(const SparseParams& P, const double*
 // columns of X; SP_LDS = 36 makes both fragment patterns below bank-conflict free: 36 = 4 mod 16 eight-byte banks).
 // lane = 4 g + c:  a = A[g][c],  b = B[c][g],  d = {D[g][2c], D[g][2c + 1]}.
 constexpr int SP_LDS = SP_SL + 4;
+constexpr int SP_ZBAR_D = 4;
+constexpr int SP_CELLS = (SP_SL + 2) / 3 + 2;   // cells touched by a slab of SP_SL columns (<= 12)
 #ifndef BGP_SP_T
 #define BGP_SP_T 512
 #endif
@@ -428,6 +430,18 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
     double* Ks = sm;                       // [Mz][33]  K(Z, x_j) of the slab
     double* Vs = sm + (size_t)Mz * LDS_;   // [Mz][33]  V of the slab
     double* Dls = Vs + (size_t)Mz * LDS_;  // [32] Delta of the slab
+    // per-row constants of the inducing inputs and per-cell values of the slab, staged once instead of being fetched from global
+    // memory for every entry (ncu: a quarter of the stall samples sat on those dependent loads)
+    double* zt_s = Dls + SP_SL;            // [Mz] inducing time
+    double* kaz_s = zt_s + Mz;             // [Mz] k(z_m, b) / (k(b,b) + jitter)
+    int* fz_s = reinterpret_cast<int*>(kaz_s + Mz);   // [Mz] function index 0..2
+    double* tc_s = kaz_s + Mz + (Mz + 1) / 2;         // [SP_CELLS] cell time
+    double* kax_s = tc_s + SP_CELLS;                  // [SP_CELLS] k(t_cell, b)
+    for (int m = tid; m < Mz; m += SP_T) {
+        zt_s[m] = P.Z[2 * m];
+        fz_s[m] = (int)P.Z[2 * m + 1] - 1;
+        kaz_s[m] = ws[SLy.kaz + m] * kinv;
+    }
     const int split = blockIdx.x, nsplit = P.nsplit;
     const double* Linv = ws + SLy.Linv;
     double* Pp = ws + SLy.Ppart + (size_t)split * Mz * Mz;
@@ -442,24 +456,21 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
         // K(Z, x_j) of the slab (branch_kernParamGPflow.py:117-198) in two divergence-free sweeps: every (inducing row, cell) pair has
         // ONE same-function column 3 cell + f_z that needs the base kernel (an exp); all other entries are products of the
         // per-row / per-cell kernels against the branching point
-        {
-            const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
-#pragma unroll 4
-            for (int e = tid; e < Mz * SP_SL; e += SP_T) {
-                const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
-                const int cell = j / 3, f = j - 3 * cell;
-                const int fz = (int)P.Z[2 * m + 1] - 1;
-                if (empty || j >= M) Ks[m * LDS_ + jj] = 0.0;
-                else if (fz != f) Ks[m * LDS_ + jj] = (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
-            }
-            if (!empty)
-                for (int e = tid; e < Mz * ncell; e += SP_T) {
-                    const int m = e / ncell, cell = cell0 + e % ncell;
-                    const int jj = 3 * cell + (int)P.Z[2 * m + 1] - 1 - j0;
-                    if (jj >= 0 && jj < SP_SL && j0 + jj < M) Ks[m * LDS_ + jj] = kbase(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind);
-                }
-        }
+        const int cell0 = j0 / 3, ncell = empty ? 0 : (min(j0 + SP_SL, M) + 2) / 3 - cell0;
+        if (tid < ncell) { tc_s[tid] = P.t[cell0 + tid]; kax_s[tid] = ws[SLy.kax + cell0 + tid]; }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
+        __syncthreads();
+        for (int e = tid; e < Mz * SP_SL; e += SP_T) {
+            const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
+            const int cell = j / 3, f = j - 3 * cell;
+            if (empty || j >= M) Ks[m * LDS_ + jj] = 0.0;
+            else if (fz_s[m] != f) Ks[m * LDS_ + jj] = kaz_s[m] * kax_s[cell - cell0];
+        }
+        for (int e = tid; e < Mz * ncell; e += SP_T) {
+            const int m = e / ncell, lc = e - m * ncell;
+            const int jj = 3 * (cell0 + lc) + fz_s[m] - j0;
+            if (jj >= 0 && jj < SP_SL && j0 + jj < M) Ks[m * LDS_ + jj] = kbase(zt_s[m] - tc_s[lc], ell, kvar, P.kind);
+        }
         __syncthreads();
         slab_mm<1>(Linv, Ks, Vs, Mz, warp, lane);   // V = Linv K(Z, X_slab)
         __syncthreads();
@@ -599,6 +610,25 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
     double* Us = sm + (size_t)Mz * LDS_;    // U, then Vbar
     double* Gs = Us + (size_t)Mz * LDS_;    // Kuf_bar
     double* Dls = Gs + (size_t)Mz * LDS_;   // Delta slab [32]
+    // staged per-row / per-cell constants (see k_sp_fwd)
+    double* zt_s = Dls + SP_SL;             // [Mz]
+    double* kaz_s = zt_s + Mz;              // [Mz] k(z_m, b)   (unscaled)
+    double* dkalz_s = kaz_s + Mz;           // [Mz]
+    double* dkabz_s = dkalz_s + Mz;         // [Mz]
+    int* fz_s = reinterpret_cast<int*>(dkabz_s + Mz);     // [Mz]
+    double* tc_s = dkabz_s + Mz + (Mz + 1) / 2;           // [SP_CELLS]
+    double* kax_s = tc_s + SP_CELLS;
+    double* dkalx_s = kax_s + SP_CELLS;
+    double* dkabx_s = dkalx_s + SP_CELLS;
+    double* zbar_st = dkabx_s + SP_CELLS;                  // [D][Mz], staged for D <= SP_ZBAR_D outputs only (shared memory budget)
+    for (int m = tid; m < Mz; m += SP_T) {
+        zt_s[m] = P.Z[2 * m];
+        fz_s[m] = (int)P.Z[2 * m + 1] - 1;
+        kaz_s[m] = ws[SLy.kaz + m]; dkalz_s[m] = ws[SLy.dkalz + m]; dkabz_s[m] = ws[SLy.dkabz + m];
+    }
+    if (D <= SP_ZBAR_D)
+        for (int e = tid; e < D * Mz; e += SP_T) zbar_st[e] = ws[SLy.zbar + e];
+    const double* zbar_s = (D <= SP_ZBAR_D) ? zbar_st : ws + SLy.zbar;
     const int split = blockIdx.x, nsplit = P.nsplit;
     const double* Pbar = ws + SLy.Pbar;
     const double* LinvT = ws + SLy.LinvT;
@@ -616,6 +646,12 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
             Vs[m * LDS_ + jj] = (!empty && j < M) ? ws[SLy.V + (size_t)m * Mp + j] : 0.0;
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
+        const int cell0 = j0 / 3, ncell = empty ? 0 : (min(j0 + SP_SL, M) + 2) / 3 - cell0;
+        if (tid >= SP_SL && tid < SP_SL + ncell) {
+            const int lc = tid - SP_SL;
+            tc_s[lc] = P.t[cell0 + lc]; kax_s[lc] = ws[SLy.kax + cell0 + lc];
+            dkalx_s[lc] = ws[SLy.dkalx + cell0 + lc]; dkabx_s[lc] = ws[SLy.dkabx + cell0 + lc];
+        }
         __syncthreads();
         slab_mm<0>(Pbar, Vs, Us, Mz, warp, lane);   // U = Pbar V
         __syncthreads();
@@ -642,7 +678,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
         for (int d = 0; d < D; ++d) {   // vbar = V^T zbar
             if (wide || warp == 0) {
                 double sacc = 0.0;
-                for (int m = wide ? warp : 0; m < Mz; m += mstep) sacc += Vs[m * LDS_ + lane] * ws[SLy.zbar + (size_t)d * Mz + m];
+                for (int m = wide ? warp : 0; m < Mz; m += mstep) sacc += Vs[m * LDS_ + lane] * zbar_s[d * Mz + m];
                 Gs[(wide ? warp : 0) * LDS_ + lane] = sacc;
             }
             __syncthreads();
@@ -658,7 +694,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
             double zv = 0.0;
             if (!empty && j < M)
-                for (int d = 0; d < D; ++d) zv += ws[SLy.zbar + (size_t)d * Mz + m] * ws[SLy.v + (size_t)d * Mp + j];
+                for (int d = 0; d < D; ++d) zv += zbar_s[d * Mz + m] * ws[SLy.v + (size_t)d * Mp + j];
             Us[m * LDS_ + jj] = Dls[jj] * (2.0 * Us[m * LDS_ + jj] + Vs[m * LDS_ + jj]) + zv;
         }
         __syncthreads();
@@ -667,25 +703,24 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
         __syncthreads();
         // hyper-gradient through K(Z, X): cross-function entries (products), then the same-function entry of every (row, cell) pair
         if (!empty) {
-#pragma unroll 4
+            const double gvf = 2.0 / kvar - kinv;
             for (int e = tid; e < Mz * SP_SL; e += SP_T) {
                 const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
                 if (j >= M) continue;
-                const int cell = j / 3, f = j - 3 * cell;
-                if ((int)P.Z[2 * m + 1] - 1 == f) continue;
-                const double w = Gs[m * LDS_ + jj];
-                const double a = ws[SLy.kaz + m], b = ws[SLy.kax + cell];
-                gl += w * (ws[SLy.dkalz + m] * b + a * ws[SLy.dkalx + cell]) * kinv;
-                gv += w * ((a * kinv) * b) * (2.0 / kvar - kinv);
-                gb += w * (ws[SLy.dkabz + m] * b + a * ws[SLy.dkabx + cell]) * kinv;
+                const int cell = j / 3, f = j - 3 * cell, lc = cell - cell0;
+                if (fz_s[m] == f) continue;
+                const double w = Gs[m * LDS_ + jj] * kinv;
+                const double a = kaz_s[m], b = kax_s[lc];
+                gl += w * (dkalz_s[m] * b + a * dkalx_s[lc]);
+                gv += w * (a * b) * gvf;
+                gb += w * (dkabz_s[m] * b + a * dkabx_s[lc]);
             }
-            const int cell0 = j0 / 3, ncell = (min(j0 + SP_SL, M) + 2) / 3 - cell0;
             for (int e = tid; e < Mz * ncell; e += SP_T) {
-                const int m = e / ncell, cell = cell0 + e % ncell;
-                const int jj = 3 * cell + (int)P.Z[2 * m + 1] - 1 - j0;
+                const int m = e / ncell, lc = e - m * ncell;
+                const int jj = 3 * (cell0 + lc) + fz_s[m] - j0;
                 if (jj < 0 || jj >= SP_SL || j0 + jj >= M) continue;
                 double k, dl, dd;
-                kbase_grads(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind, k, dl, dd);
+                kbase_grads(zt_s[m] - tc_s[lc], ell, kvar, P.kind, k, dl, dd);
                 const double w = Gs[m * LDS_ + jj];
                 gl += w * dl;
                 gv += w * k / kvar;
@@ -930,7 +965,8 @@ void sparse_launch_predict(const SparseParams& P, const double* Xnew, int T, int
 static size_t packed_bytes(int Mz) {   // packed lower triangle + inverse diagonal blocks + 8 x 9 scratch per warp
     return ((size_t)Mz * (Mz + 1) / 2 + 64 * (size_t)((Mz + 7) / 8) + 72 * (SP_T / 32)) * 8;
 }
-static size_t slab_bytes(int Mz, int nbuf) { return ((size_t)nbuf * Mz * SP_LDS + SP_SL) * 8; }
+// slab buffers + Delta + staged vectors (k_sp_fwd: 2 per-row vectors + fz; k_sp_bwd: 4 + fz + zbar; 4 per-cell vectors)
+static size_t slab_bytes(int Mz, int nbuf, int D) { return ((size_t)nbuf * Mz * SP_LDS + SP_SL + 5 * (size_t)Mz + (size_t)(D <= SP_ZBAR_D ? D : 0) * Mz + 4 * SP_CELLS + 8) * 8; }
 
 cudaError_t sparse_init_kernels() {
     cudaError_t e;
@@ -951,9 +987,9 @@ void sparse_launch_phase(const SparseParams& P, int nslots, int phase, double* s
             k_sp_prep<<<g1, NTHREADS, 0, st>>>(P);
             break;
         case 1: k_sp_kuu<<<g1, SP_T, packed_bytes(P.Mz), st>>>(P); break;
-        case 2: k_sp_fwd<<<gs, SP_T, slab_bytes(P.Mz, 2), st>>>(P); break;
+        case 2: k_sp_fwd<<<gs, SP_T, slab_bytes(P.Mz, 2, P.D), st>>>(P); break;
         case 3: k_sp_mid<<<g1, SP_T, packed_bytes(P.Mz), st>>>(P); break;
-        case 4: k_sp_bwd<<<gs, SP_T, slab_bytes(P.Mz, 3), st>>>(P); break;
+        case 4: k_sp_bwd<<<gs, SP_T, slab_bytes(P.Mz, 3, P.D), st>>>(P); break;
         case 5: {
             k_sp_end<<<g1, SP_END_THREADS, 0, st>>>(P, sub_out);
             const int nitems = nslots / P.SD;
