@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
     double* Dls = Vs + (size_t)Mz * LDS_;  // [32] Delta of the slab
     // per-row constants of the inducing inputs and per-cell values of the slab, staged once instead of being fetched from global
     // memory for every entry (ncu: a quarter of the stall samples sat on those dependent loads)
-    double* zt_s = Dls + SP_SL;            // [Mz] inducing time
+    double* vsl_s = Dls + SP_SL;           // [SP_ZBAR_D][32] v of the slab (outputs beyond SP_ZBAR_D are read from global memory)
+    double* zt_s = vsl_s + SP_ZBAR_D * SP_SL;   // [Mz] inducing time
     double* kaz_s = zt_s + Mz;             // [Mz] k(z_m, b) / (k(b,b) + jitter)
     int* fz_s = reinterpret_cast<int*>(kaz_s + Mz);   // [Mz] function index 0..2
     double* tc_s = kaz_s + Mz + (Mz + 1) / 2;         // [SP_CELLS] cell time
@@ -459,6 +460,10 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
         const int cell0 = j0 / 3, ncell = empty ? 0 : (min(j0 + SP_SL, M) + 2) / 3 - cell0;
         if (tid < ncell) { tc_s[tid] = P.t[cell0 + tid]; kax_s[tid] = ws[SLy.kax + cell0 + tid]; }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
+        if (tid >= 64 && tid < 64 + SP_ZBAR_D * SP_SL) {
+            const int d = (tid - 64) / SP_SL, jj = (tid - 64) % SP_SL;
+            vsl_s[d * SP_SL + jj] = (d < D && !empty && j0 + jj < M) ? ws[SLy.v + (size_t)d * Mp + j0 + jj] : 0.0;
+        }
         __syncthreads();
         for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
@@ -490,9 +495,15 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
         for (int e = tid; e < D * Mz; e += SP_T) {
             const int d = e / Mz, m = e % Mz;
             double s = 0.0;
-            if (!empty)
-                for (int jj = 0; jj < SP_SL; ++jj)
-                    if (j0 + jj < M) s += Vs[m * LDS_ + jj] * ws[SLy.v + (size_t)d * Mp + j0 + jj];
+            if (!empty) {
+                if (d < SP_ZBAR_D) {
+#pragma unroll 8
+                    for (int jj = 0; jj < SP_SL; ++jj) s += Vs[m * LDS_ + jj] * vsl_s[d * SP_SL + jj];   // (columns >= M hold zeros)
+                } else {
+                    for (int jj = 0; jj < SP_SL; ++jj)
+                        if (j0 + jj < M) s += Vs[m * LDS_ + jj] * ws[SLy.v + (size_t)d * Mp + j0 + jj];
+                }
+            }
             zp[e] = first ? s : (zp[e] + s);
         }
         first = false;
@@ -611,7 +622,8 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
     double* Gs = Us + (size_t)Mz * LDS_;    // Kuf_bar
     double* Dls = Gs + (size_t)Mz * LDS_;   // Delta slab [32]
     // staged per-row / per-cell constants (see k_sp_fwd)
-    double* zt_s = Dls + SP_SL;             // [Mz]
+    double* vsl_s = Dls + SP_SL;            // [SP_ZBAR_D][32] v of the slab
+    double* zt_s = vsl_s + SP_ZBAR_D * SP_SL;   // [Mz]
     double* kaz_s = zt_s + Mz;              // [Mz] k(z_m, b)   (unscaled)
     double* dkalz_s = kaz_s + Mz;           // [Mz]
     double* dkabz_s = dkalz_s + Mz;         // [Mz]
@@ -647,6 +659,10 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
         }
         if (tid < SP_SL) Dls[tid] = (!empty && j0 + tid < M) ? ws[SLy.Delta + j0 + tid] : 0.0;
         const int cell0 = j0 / 3, ncell = empty ? 0 : (min(j0 + SP_SL, M) + 2) / 3 - cell0;
+        if (tid >= 64 && tid < 64 + SP_ZBAR_D * SP_SL) {
+            const int d = (tid - 64) / SP_SL, jj = (tid - 64) % SP_SL;
+            vsl_s[d * SP_SL + jj] = (d < D && !empty && j0 + jj < M) ? ws[SLy.v + (size_t)d * Mp + j0 + jj] : 0.0;
+        }
         if (tid >= SP_SL && tid < SP_SL + ncell) {
             const int lc = tid - SP_SL;
             tc_s[lc] = P.t[cell0 + lc]; kax_s[lc] = ws[SLy.kax + cell0 + lc];
@@ -694,7 +710,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
             double zv = 0.0;
             if (!empty && j < M)
-                for (int d = 0; d < D; ++d) zv += zbar_s[d * Mz + m] * ws[SLy.v + (size_t)d * Mp + j];
+                for (int d = 0; d < D; ++d) zv += zbar_s[d * Mz + m] * (d < SP_ZBAR_D ? vsl_s[d * SP_SL + jj] : ws[SLy.v + (size_t)d * Mp + j]);
             Us[m * LDS_ + jj] = Dls[jj] * (2.0 * Us[m * LDS_ + jj] + Vs[m * LDS_ + jj]) + zv;
         }
         __syncthreads();
@@ -966,7 +982,7 @@ static size_t packed_bytes(int Mz) {   // packed lower triangle + inverse diagon
     return ((size_t)Mz * (Mz + 1) / 2 + 64 * (size_t)((Mz + 7) / 8) + 72 * (SP_T / 32)) * 8;
 }
 // slab buffers + Delta + staged vectors (k_sp_fwd: 2 per-row vectors + fz; k_sp_bwd: 4 + fz + zbar; 4 per-cell vectors)
-static size_t slab_bytes(int Mz, int nbuf, int D) { return ((size_t)nbuf * Mz * SP_LDS + SP_SL + 5 * (size_t)Mz + (size_t)(D <= SP_ZBAR_D ? D : 0) * Mz + 4 * SP_CELLS + 8) * 8; }
+static size_t slab_bytes(int Mz, int nbuf, int D) { return ((size_t)nbuf * Mz * SP_LDS + SP_SL + 5 * (size_t)Mz + (size_t)(D <= SP_ZBAR_D ? D : 0) * Mz + 4 * SP_CELLS + SP_ZBAR_D * SP_SL + 8) * 8; }
 
 cudaError_t sparse_init_kernels() {
     cudaError_t e;
