@@ -826,8 +826,11 @@ struct StreamRing {
     }
 };
 
+#ifndef BGP_FWD_MINB
+#define BGP_FWD_MINB 3
+#endif
 template <bool TMA>
-__global__ void __launch_bounds__(NTHREADS, 3) k_phi_fwd_stream_bgp(PhiParams P) {
+__global__ void __launch_bounds__(NTHREADS, BGP_FWD_MINB) k_phi_fwd_stream_bgp(PhiParams P) {
     __shared__ double lse_s[PHI_SRCH], y_s[PHI_SRCH], cw[SW][PHI_SRCH], red[32];
     __shared__ int act_s[PHI_SRCH];
     __shared__ __align__(128) double ring_s[TMA ? SNST * PHI_SCOLS : 1];

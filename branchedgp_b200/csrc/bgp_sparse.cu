@@ -6,7 +6,8 @@
 //   gradient = SURVEY.md App. B.2.
 // Matrices are Mz x Mz (Mz = 30 for BGP, 180 for MBGP): they are factored / inverted in shared memory (packed lower
 // triangle) by one CTA per sub-problem, while the 3N columns of X are streamed in slabs of 32 with K(Z, x_j) generated
-// in-kernel.  The O(N * 3N) assignment passes (bgp_phi.cu) dominate at the sizes the reference uses.
+// in-kernel.  Every GEMM-shaped piece (slab products, blocked Cholesky / inverse, the triangular products of the Kuu adjoint) runs on
+// the fp64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA).  The O(N * 3N) assignment passes (bgp_phi.cu) dominate the sparse BGP sizes.
 #include "bgp_sparse.cuh"
 #include "bgp_dense.cuh"
 #include "bgp_launch.h"
@@ -28,47 +29,7 @@ namespace bgp {
 
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, j <= i
 
-// In-place lower Cholesky of a packed matrix in shared memory.
-__device__ void chol_packed(double* A, int n, int& fail) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = 0; j < n; ++j) {
-        __syncthreads();
-        double d = A[pk(j, j)];
-        if (!(d > 0.0)) { if (fail == 0) fail = j + 1; d = 1.0; }
-        const double r = sqrt(d);
-        __syncthreads();
-        if (tid == 0) A[pk(j, j)] = r;
-        for (int i = j + 1 + tid; i < n; i += nt) A[pk(i, j)] /= r;
-        __syncthreads();
-        for (int i = j + 1 + (tid >> 4); i < n; i += nt >> 4) {
-            const double lij = A[pk(i, j)];
-            for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[pk(i, k)] -= lij * A[pk(k, j)];
-        }
-    }
-    __syncthreads();
-}
-
-// In-place inverse of a packed lower-triangular matrix in shared memory (two threads per column).
-__device__ void trinv_packed(double* A, int n) {
-    const int tid = threadIdx.x;
-    const int nt = blockDim.x;
-    for (int i = 0; i < n; ++i) {
-        const double lii = A[pk(i, i)];
-        for (int j0 = 0; j0 <= i; j0 += nt / 2) {   // columns handled in rounds when n > nt/2
-            const int j = j0 + (tid >> 1), h = tid & 1;
-            double s = 0.0;
-            if (j < i)
-                for (int k = j + h; k < i; k += 2) s += A[pk(i, k)] * A[pk(k, j)];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const double x = (j < i) ? (-s / lii) : (1.0 / lii);
-            __syncthreads();
-            if (h == 0 && j <= i) A[pk(i, j)] = x;
-            __syncthreads();
-        }
-    }
-}
-
-// ---- blocked versions on the fp64 tensor pipe (8 x 8 blocks = one DMMA tile; the packed layout is addressed element by element,
+// ---- Cholesky / inverse of a packed lower-triangular matrix in shared memory on the fp64 tensor pipe (8 x 8 blocks = one DMMA tile; the packed layout is addressed element by element,
 // which is all a DMMA fragment needs).  `dinv` receives the inverses of the diagonal blocks ([blocks][64], zero above the
 // diagonal and in the padding of a ragged last block); the inverse routine reuses them.
 __device__ __forceinline__ int pk_blocks(int n) { return (n + 7) >> 3; }
@@ -270,15 +231,6 @@ __global__ void __launch_bounds__(NTHREADS) k_sp_prep(SparseParams P) {
         ws[SLy.scal + SS_KL] = kl; ws[SLy.scal + SS_SUMY2] = y2; ws[SLy.scal + SS_SUMA] = suma;
         if (sd == 0) P.status[item] = 0;
     }
-}
-
-// covariance between inducing row m and column j of X (cell-major), branch_kernParamGPflow.py:117-198
-__device__ __forceinline__ double kuf_entry(const SparseParams& P, const double* ws, const SparseLayout& SLy, int m, int j, double ell,
-                                            double kvar, double kinv) {
-    const int cell = j / 3, f = j - 3 * cell;
-    const int fz = (int)P.Z[2 * m + 1] - 1;
-    if (fz == f) return kbase(P.Z[2 * m] - P.t[cell], ell, kvar, P.kind);
-    return (ws[SLy.kaz + m] * kinv) * ws[SLy.kax + cell];
 }
 
 // Slab products on the fp64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA): a slab is [Mz][SP_LDS] in shared memory (SP_SL = 32

@@ -66,3 +66,32 @@ tail = log_emul(ys[-2004:]); reft = np.array([float(mp.log(mp.mpf(float(v)))) fo
 print("log near 1: max abs err", np.max(np.abs(tail - reft)))
 np.save("/tmp/rtab.npy", np.array(rtab)); np.save("/tmp/ltab.npy", np.array(ltab))
 open("/tmp/tab.txt", "w").write(",\n".join("    {%.17g, %.17g}" % (r, l) for r, l in zip(rtab, ltab)))
+
+# ---- table exp (the shipped fast_exp): x = (32 n + j) ln2/32 + r, exp x = 2^n T[j] (1 + r h(r)), T[j] = 2^(j/32), degree-5 h
+import struct
+Kt = 32
+ln2_K = mp.log(2) / Kt
+hi = float(ln2_K)
+bits = struct.unpack('<Q', struct.pack('<d', hi))[0] & ~((1 << 17) - 1)      # 36 significant bits: n * hi is exact for |n| < 2^16
+hi = struct.unpack('<d', struct.pack('<Q', bits))[0]
+lo = float(ln2_K - mp.mpf(hi))
+inv = float(Kt / mp.log(2))
+ttab = [float(mp.mpf(2) ** (mp.mpf(j) / Kt)) for j in range(Kt)]
+print("table exp constants: 32/ln2 = %.17g, ln2/32 hi = %.17g, lo = %.17g" % (inv, hi, lo))
+print("T[j]:", ", ".join("%.17g" % v for v in ttab))
+hc = [1.0, 0.5, 1 / 6, 1 / 24, 1 / 120, 1 / 720]
+def exp_table_emul(x):
+    x = np.asarray(x, dtype=np.float64)
+    n = np.rint(x * inv)
+    r = np.longdouble(x) - np.longdouble(n) * np.longdouble(hi)
+    r = (r - np.longdouble(n) * np.longdouble(lo)).astype(np.float64)
+    h = np.full_like(r, hc[5])
+    for k in range(4, -1, -1):
+        h = h * r + hc[k]
+    ni = n.astype(np.int64)
+    T = np.array(ttab)[ni & 31]
+    y = (np.longdouble(T) * np.longdouble(r * h) + np.longdouble(T)).astype(np.float64)
+    return np.ldexp(y, (ni >> 5).astype(int))
+xt = np.concatenate([-np.abs(np.random.default_rng(0).standard_normal(20000)) * 30, -np.random.default_rng(1).uniform(0, 700, 20000)])
+reft = np.array([float(mp.e ** mp.mpf(float(v))) for v in xt])
+print("table exp max rel err (vs mpmath, 40000 pts):", np.max(np.abs(exp_table_emul(xt) - reft) / reft))
