@@ -255,8 +255,9 @@ __device__ __forceinline__ void slab_mm(const double* __restrict__ A, const doub
     // 8-row tiles dealt to the warps in snake order (w, 15 - w, 16 + w, ...): the triangular k ranges add up evenly
     for (int i = 0; (i >> 1) * 2 * SP_WARPS < nrt; ++i) {
         const int base = (i >> 1) * 2 * SP_WARPS;
-        const int rt = (i & 1) ? base + 2 * SP_WARPS - 1 - warp : base + warp;
-        if (rt >= nrt) continue;
+        const int js = (i & 1) ? base + 2 * SP_WARPS - 1 - warp : base + warp;
+        if (js >= nrt) continue;
+        const int rt = (TRI == 1) ? nrt - 1 - js : js;   // longest k ranges first: k <= m grows with the row tile, k >= m shrinks
         const int m = rt * 8 + g;
         const bool vm = m < Mz;
         const double* pa = A + (size_t)min(m, Mz - 1) * Mz + c;
