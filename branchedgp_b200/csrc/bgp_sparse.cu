@@ -52,6 +52,7 @@ __device__ void chol_packed_blocked(double* A, int n, int& fail, double* dinv) {
             double a[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) a[k] = (lane < w && k <= lane) ? A[pk(j0 + lane, j0 + k)] : ((k == lane) ? 1.0 : 0.0);
+            double rinv[8];   // reciprocal pivots: one rsqrt per column, no square root or division on this serial path
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 double sacc = a[j];
@@ -62,8 +63,8 @@ __device__ void chol_packed_blocked(double* A, int n, int& fail, double* dinv) {
                     if (lane == 0 && fail_s == 0) fail_s = j0 + j + 1;
                     d = 1.0;
                 }
-                const double r = sqrt(d);
-                a[j] = (lane < j) ? 0.0 : ((lane == j) ? r : sacc / r);
+                rinv[j] = rsqrt(d);
+                a[j] = (lane < j) ? 0.0 : ((lane == j) ? d * rinv[j] : sacc * rinv[j]);
             }
             double x[8];   // lane = column of the inverse
 #pragma unroll
@@ -71,8 +72,7 @@ __device__ void chol_packed_blocked(double* A, int n, int& fail, double* dinv) {
                 double sacc = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
                 for (int k = 0; k < i; ++k) sacc = fma(-__shfl_sync(0xffffffffu, a[k], i), x[k], sacc);
-                const double lii = __shfl_sync(0xffffffffu, a[i], i);
-                x[i] = (i >= lane) ? sacc / lii : 0.0;
+                x[i] = (i >= lane) ? sacc * rinv[i] : 0.0;
             }
             if (lane < 8) {
 #pragma unroll
@@ -741,7 +741,7 @@ __device__ __forceinline__ void gmm_tri(const double* __restrict__ A, const doub
             const int kk = k + c, n = n0 + 8 * t + g;
             return (kk < Mz && n < Mz) ? B[(size_t)kk * Mz + n] : 0.0;
         };
-        double an = lda(k0), bn[4];
+        double an = lda(k0), bn[4];   // one k step ahead (three steps ahead measured slower: 0.77 against 0.66 ms at Mz = 180)
 #pragma unroll
         for (int t = 0; t < 4; ++t) bn[t] = ldb(k0, t);
         for (int k = k0; k < k1; k += 4) {
