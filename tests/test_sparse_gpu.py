@@ -121,6 +121,9 @@ def test_long_rows_streaming_and_row_resident_passes_agree(engine, monkeypatch):
         monkeypatch.setenv("BGP_PHI_STREAM", flag)
         outs.append(engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"]))
     monkeypatch.delenv("BGP_PHI_STREAM")
+    monkeypatch.setenv("BGP_PHI_TMA", "0")   # streams with register prefetch instead of the TMA row ring (what odd 3N falls back to)
+    outs.append(engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"]))
+    monkeypatch.delenv("BGP_PHI_TMA")
     for k in range(pr["count"]):
         b, h = pr["b"][k], pr["hyp"][k]
         e, g = bgp_numpy.sparse_value_and_grad(pr["logPhi"][k], pr["Y"][pr["item_gene"][k]], pr["X"], Z, _pz(pr, b), b, h[0], h[1], h[2])
@@ -133,3 +136,37 @@ def test_long_rows_streaming_and_row_resident_passes_agree(engine, monkeypatch):
                 assert abs(out["grad_hyp"][k, j] - g[nm]) <= GRAD_RTOL * max(abs(g[nm]), 1e-3 * scale)
         assert abs(outs[0]["elbo"][k] - outs[1]["elbo"][k]) <= 1e-12 * abs(e)
         assert relerr(outs[0]["grad_logPhi"][k], outs[1]["grad_logPhi"][k]) <= 1e-11
+        assert abs(outs[0]["elbo"][k] - outs[2]["elbo"][k]) <= 1e-14 * abs(e)            # same arithmetic, different data movement
+        assert relerr(outs[0]["grad_logPhi"][k], outs[2]["grad_logPhi"][k]) <= 1e-13
+
+
+def test_long_rows_odd_width_and_mbgp_single_output_streams(engine):
+    """The two remaining stream variants against the oracle: an odd row length (N = 2051, 3N = 6153: row pieces are not 16-byte
+    aligned, so the streams prefetch through registers) for sparse BGP, and the general (non-BGP) element code for an MBGP model
+    with one output (N = 2100; trunk rows carry no gradient)."""
+    N = 2051
+    pr = make_problem(N, D=1, n_genes=1, bs=(0.4,), seed=83)
+    Z = _Z(12)
+    b, h = pr["b"][0], pr["hyp"][0]
+    e, g = bgp_numpy.sparse_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], Z, _pz(pr, b), b, h[0], h[1], h[2])
+    out = engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"])
+    assert out["status"][0] == 0
+    assert abs(out["elbo"][0] - e) <= ELBO_RTOL * abs(e), (out["elbo"][0], e)
+    assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
+
+    N = 2100
+    pr = make_problem(N, D=1, seed=84, mbgp=True)
+    t = pr["t"]
+    _, trunk = host_ref.init_logphi_mbgp(pr["phi0"], t)
+    eZ0 = host_ref.expand_prior_mbgp(pr["prior3"])
+    Zt = np.linspace(0, 1, 8, endpoint=False)
+    Zm = np.array([[z, f] for z in Zt for f in (1, 2, 3)], dtype=float)
+    Bv = np.array([0.45])
+    hm = np.array([[0.7, 1.3, 0.2]])
+    e, g = bgp_numpy.mbgp_sparse_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], Zm, t, eZ0, trunk, Bv, hm[0, 0], hm[0, 1], hm[0, 2])
+    out = engine.sparse_elbo_grad(t, Zm, pr["Y"], pr["item_gene"][:1], Bv[None], pr["prior3"], hm, pr["logPhi"][:1],
+                                  kernel=_lib.KERNEL_SQEXP, model=_lib.MODEL_MBGP, multi=True)
+    assert out["status"][0] == 0
+    assert abs(out["elbo"][0] - e) <= ELBO_RTOL * abs(e), (out["elbo"][0], e)
+    assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
+    assert relerr(out["grad_b"][0], g["Bv"]) <= GRAD_RTOL
