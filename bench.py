@@ -336,8 +336,22 @@ def run_ours(args):
                              "D (4 Mz^2 3N + Mz^3) over the measured DMMA peak",
                      "C3": time_sparse.run("C3 sparse BGP: N=10000, Mz=30", 10000, 1, 30, 8, False, eng=eng, verbose=False),
                      "C4": time_sparse.run("C4 MBGP: N=500, D=100, Mz=180", 500, 100, 180, 4, True, eng=eng, verbose=False)}
+            # C1 (BASELINE.json configs[0]): the drop-in FitModel call on one synthetic gene, N = 100, 10-point grid -- wall
+            # clock of the whole call through the public API, SciPy driver and device-resident batched optimiser
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from golden.make_golden_c1 import MAXITER, c1_problem
+            from branchedgp_b200 import FitBranchingModel
+            t1, Y1, lab1, grid1 = c1_problem()
+            c1 = {"config": "C1: FitModel, 1 gene, N=100, 10 grid points, maxiter=%d, trainable hyper-parameters" % MAXITER}
+            for name, fn in (("FitModel_scipy_driver", lambda: FitBranchingModel.FitModel(grid1, t1, Y1, lab1, M=0, maxiter=MAXITER)),
+                             ("FitModelBatch_device_optimiser", lambda: FitBranchingModel.FitModelBatch(grid1, t1, Y1, lab1, M=0, maxiter=MAXITER)[0])):
+                fn()   # warm-up (workspace allocation)
+                t0 = time.perf_counter()
+                r1 = fn()
+                c1[name] = {"seconds": round(time.perf_counter() - t0, 3), "argmax_b": round(float(grid1[int(np.argmax(r1["loglik"]))]), 6)}
+            other["C1"] = c1
         except Exception as exc:   # never lose the headline line to a side measurement
-            other = {"error": repr(exc)}
+            other = {"error": repr(exc)} if other is None else dict(other, error=repr(exc))
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
