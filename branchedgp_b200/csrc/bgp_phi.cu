@@ -1034,6 +1034,99 @@ static bool params_streaming(const PhiParams& P) {
     return rch <= PHI_SRCH && phi_streaming(P.N, P.M, P.SD, P.D, P.grad_logPhi != nullptr, rch) && P.rowpart != nullptr;
 }
 
+
+// MBGP multi-output backward pass, MB_R rows per CTA: the per-element sum over the outputs that treat the row as a branch row,
+//     acc_ij = sum_{d: t_i > b_d} (Abar_d[j] + Y_id vbar_d[j]),
+// reads two vectors per output and column; with one row per CTA that is 2 SD M doubles from L2 per row (ncu: the pass was L2
+// bound).  Here every pair (Abar_d[j], vbar_d[j]) fetched by a thread feeds MB_R rows.  Rows fit the CTA: M <= MB_BT * MB_EPT.
+constexpr int MB_R = 4, MB_BT = 256, MB_EPT = 6;
+__global__ void __launch_bounds__(MB_BT) k_phi_backward_rows_multi(PhiParams P) {
+    __shared__ double y_s[MB_R][MO_MAXSD], bv_s[MO_MAXSD], t_s[MB_R], red[32];
+    __shared__ int nact_s[MB_R];
+    const int tid = threadIdx.x;
+    const int litem = blockIdx.y, item = P.item0 + litem;
+    const int N = P.N, M = P.M, SD = P.SD;
+    const int r0 = blockIdx.x * MB_R, nr = min(MB_R, N - r0);
+    const size_t slot0 = (size_t)litem * SD;
+    const double* Yg = P.Y + (size_t)P.item_gene[item] * N * P.Dtot;
+    const double* prior = P.prior;
+    double* gout = P.grad_logPhi + ((size_t)item * N + r0) * M;
+    for (int e = tid; e < MB_R * SD; e += MB_BT) {
+        const int r = e / SD, sd = e - r * SD;
+        y_s[r][sd] = r < nr ? Yg[(size_t)(r0 + r) * P.Dtot + sd] : 0.0;
+    }
+    for (int sd = tid; sd < SD; sd += MB_BT) bv_s[sd] = P.bv[(size_t)item * SD + sd];
+    if (tid < MB_R) t_s[tid] = tid < nr ? P.t[r0 + tid] : -1.0e308;
+    __syncthreads();
+    if (tid < MB_R) {
+        int na = 0;
+        for (int sd = 0; sd < SD; ++sd) na += t_s[tid] > bv_s[sd] ? 1 : 0;
+        nact_s[tid] = na;
+    }
+    double acc[MB_R][MB_EPT], S[MB_R][MB_EPT];
+#pragma unroll
+    for (int r = 0; r < MB_R; ++r)
+#pragma unroll
+        for (int e = 0; e < MB_EPT; ++e) acc[r][e] = 0.0;
+    for (int sd = 0; sd < SD; ++sd) {
+        const double b = bv_s[sd];
+        const double* Abar = P.Abar + (slot0 + sd) * P.slot_stride;
+        const double* vbar = P.vbar + (slot0 + sd) * P.slot_stride;
+        double A[MB_EPT], V[MB_EPT];
+#pragma unroll
+        for (int e = 0; e < MB_EPT; ++e) {
+            const int j = tid + e * MB_BT;
+            A[e] = j < M ? Abar[j] : 0.0;
+            V[e] = j < M ? vbar[j] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < MB_R; ++r) {
+            if (t_s[r] > b) {   // uniform over the CTA
+                const double y = y_s[r][sd];
+#pragma unroll
+                for (int e = 0; e < MB_EPT; ++e) acc[r][e] += fma(y, V[e], A[e]);
+            }
+        }
+    }
+    __syncthreads();   // nact_s
+    const double lpz_off = log(SQ_A * 1e-6 + SQ_B);
+    double rs[MB_R];
+#pragma unroll
+    for (int r = 0; r < MB_R; ++r) {
+        rs[r] = 0.0;
+        const int row = r0 + r;
+        const double klw = P.kl_weight * (double)nact_s[r];
+#pragma unroll
+        for (int e = 0; e < MB_EPT; ++e) {
+            const int j = tid + e * MB_BT;
+            S[r][e] = 0.0;
+            if (r < nr && j < M) {
+                const int f = j - 3 * row;
+                const bool inblock = (f >= 0 && f < 3);
+                const double s_ = gout[(size_t)r * M + j];   // softmax value stashed by the forward pass
+                const double lpz = inblock ? log_pz(MODEL_MBGP, true, true, f, prior, row, 0.0) : lpz_off;
+                const double v = SQ_A * (acc[r][e] - klw * (fast_log(fma(SQ_A, s_, SQ_B)) + 1.0 - lpz));
+                S[r][e] = s_;
+                acc[r][e] = v;
+                rs[r] = fma(s_, v, rs[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MB_R; ++r) rs[r] = block_sum(rs[r], red);
+#pragma unroll
+    for (int r = 0; r < MB_R; ++r) {
+        if (r < nr) {
+            const bool live = nact_s[r] > 0;   // trunk rows of every output carry no gradient
+#pragma unroll
+            for (int e = 0; e < MB_EPT; ++e) {
+                const int j = tid + e * MB_BT;
+                if (j < M) gout[(size_t)r * M + j] = live ? S[r][e] * (acc[r][e] - rs[r]) : 0.0;
+            }
+        }
+    }
+}
+
 template <int BT, int EPT, int MINB, int CL>
 static void launch_rows_cluster(const PhiParams& P, int nitems, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
@@ -1091,6 +1184,13 @@ void phi_launch_backward(const PhiParams& P, int nitems, cudaStream_t st) {
         return;
     }
     const bool simple = (P.SD == 1 && P.D == 1);
+    {
+        const char* mo = getenv("BGP_PHI_MULTI");
+        if (P.SD > 1 && P.SD <= MO_MAXSD && P.D == 1 && P.model == MODEL_MBGP && P.M <= MB_BT * MB_EPT && !(mo && mo[0] == '0')) {
+            k_phi_backward_rows_multi<<<dim3((P.N + MB_R - 1) / MB_R, nitems), MB_BT, 0, st>>>(P);
+            return;
+        }
+    }
     if (P.M <= 256 * 4) {
         if (simple) k_phi_backward_rows<256, 4, 4, 1, true><<<rows, 256, 0, st>>>(P);
         else k_phi_backward_rows<256, 4, 4, 1, false><<<rows, 256, 0, st>>>(P);
