@@ -146,6 +146,7 @@ def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=
     pred_mu = np.empty((G, B, 300, 1)) if fPredict else None
     pred_var = np.empty((G, B, 300)) if fPredict else None
     failed = np.zeros(G, dtype=bool)
+    failed_at = np.full(G, B, dtype=int)      # first grid index whose factorisation failed
     fit_info = [dict(iters=np.zeros(B, dtype=int), nfev=np.zeros(B, dtype=int), status=np.zeros(B, dtype=int)) for _ in range(G)]
 
     def run(genes, ibs, hyp0):
@@ -161,6 +162,8 @@ def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=
                 pred_var[g, ib] = out["pred_var"][k]
             for key in ("iters", "nfev", "status"):
                 fit_info[g][key][ib] = out[key][k]
+            if out["status"][k] == 5:
+                failed_at[g] = min(failed_at[g], int(ib))
             if out["status"][k] == 5 and not failed[g]:
                 failed[g] = True
                 print(f"Unexpected error: Cholesky decomposition was not successful (gene {g}, b={bConsider[ib]})")
@@ -182,7 +185,10 @@ def FitModelBatch(bConsider, GPt, GPY, globalBranching, priorConfidence=0.80, M=
     results = []
     for g in range(G):
         if failed[g]:
-            bad = np.zeros(B)
+            # FitModel's error branch (FitBranchingModel.py:142-153): the grid entries computed before the failing point are kept,
+            # the failing one and everything after it stay zero, and only ll[0] is overwritten with NaN
+            bad = ll[g].copy()
+            bad[failed_at[g]:] = 0.0
             bad[0] = np.nan
             results.append({"loglik": bad, "model": None, "Phi": np.nan, "prediction": {"xtest": np.nan, "mu": np.nan, "var": np.nan},
                             "hyperparameters": np.nan, "posteriorB": np.nan, "fit": fit_info[g]})

@@ -38,6 +38,12 @@ def main():
         out[name + "/hyp"] = r["hyperparameters"]
         out[name + "/hyp_all"] = r["hyp_all"]
         print(name, r["loglik"], r["hyperparameters"])
+    # the first grid point on its own (trainable hyper-parameters): no warm-start chain has amplified anything yet, so the
+    # assignment probabilities there are held to north_star's 1e-6
+    r = fit_ref.fit_model(grid[:1], t, Y, labels, M=0, maxiter=MAXITER, fixHyperparameters=False)
+    out["train_first/loglik"] = r["loglik"]
+    out["train_first/Phi"] = r["Phi"]
+    out["train_first/hyp"] = r["hyperparameters"]
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c1_fitmodel.npz"), **out)
 
 

@@ -222,7 +222,8 @@ def test_c5_shape_n2000_item_matches_oracle_and_properties(engine):
 
 def test_dense_long_rows_streaming_passes(engine, monkeypatch):
     """N = 2100 (rows of 6300 columns, beyond one CTA's registers): the streaming assignment passes (16-row chunks in the dense
-    workspace) against the two-pass / cluster kernels they replace (BGP_PHI_STREAM=0), plus the zero row sums of a softmax gradient."""
+    workspace) AND the two-pass / cluster kernels they replace (BGP_PHI_STREAM=0), both against the numpy oracle, plus the
+    zero row sums of a softmax gradient."""
     pr = make_problem(2100, D=1, n_genes=1, bs=(0.55,), seed=19)
     args = (pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"])
     outs = []
@@ -231,9 +232,13 @@ def test_dense_long_rows_streaming_passes(engine, monkeypatch):
         outs.append(engine.dense_elbo_grad(*args, pr["hyp"], pr["logPhi"]))
     monkeypatch.delenv("BGP_PHI_STREAM")
     a, b = outs
-    assert a["status"][0] == 0 and b["status"][0] == 0
+    bb, h = pr["b"][0], pr["hyp"][0]
+    e, g = bgp_numpy.dense_value_and_grad(pr["logPhi"][0], pr["Y"][0], pr["X"], _pz(pr, bb), bb, h[0], h[1], h[2])
+    for out in outs:
+        assert out["status"][0] == 0
+        _check_item(out, 0, e, g)
     assert abs(a["elbo"][0] - b["elbo"][0]) <= 1e-12 * abs(b["elbo"][0])
     assert relerr(a["grad_logPhi"][0], b["grad_logPhi"][0]) <= 1e-10
     assert np.allclose(a["grad_hyp"], b["grad_hyp"], rtol=1e-9, atol=0)
-    g = a["grad_logPhi"][0]
-    assert np.abs(g.sum(axis=1)).max() <= 1e-9 * np.abs(g).sum(axis=1).max()
+    gl = a["grad_logPhi"][0]
+    assert np.abs(gl.sum(axis=1)).max() <= 1e-9 * np.abs(gl).sum(axis=1).max()

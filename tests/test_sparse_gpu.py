@@ -170,3 +170,32 @@ def test_long_rows_odd_width_and_mbgp_single_output_streams(engine):
     assert abs(out["elbo"][0] - e) <= ELBO_RTOL * abs(e), (out["elbo"][0], e)
     assert relerr(out["grad_logPhi"][0], g["logPhi"]) <= GRAD_RTOL
     assert relerr(out["grad_b"][0], g["Bv"]) <= GRAD_RTOL
+
+
+def test_c3_full_shape_n10000_mz30_matches_oracle(engine):
+    """BASELINE configs[2] at its real shape: N = 10 000 cells (rows of 30 000 columns, 2.4 GB of logPhi per item), 30 inducing
+    points.  This is the size where the streams run many row chunks x column chunks and byte offsets pass 2^31.  ELBO to 1e-8,
+    hyper-gradients and the FULL logPhi gradient to 1e-6 against oracle.bgp_numpy (restatement of assigngp_denseSparse.py:59-107;
+    oracle = restatement, parity unpinned by the reference).  Two items in one call so that the second one's offsets are exercised
+    too; the second is checked through its ELBO and 1000 random gradient rows against a second oracle evaluation."""
+    N = 10000
+    pr = make_problem(N, D=1, n_genes=1, bs=(0.45, 0.7), seed=79)
+    Z = _Z(30)
+    out = engine.sparse_elbo_grad(pr["t"], Z, pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"])
+    rows = np.random.default_rng(0).choice(N, 1000, replace=False)
+    for k in range(2):
+        b, h = pr["b"][k], pr["hyp"][k]
+        e, g = bgp_numpy.sparse_value_and_grad(pr["logPhi"][k], pr["Y"][0], pr["X"], Z, _pz(pr, b), b, h[0], h[1], h[2])
+        assert out["status"][k] == 0
+        assert abs(out["elbo"][k] - e) <= ELBO_RTOL * abs(e), (out["elbo"][k], e)
+        if k == 0:
+            assert relerr(out["grad_logPhi"][k], g["logPhi"]) <= GRAD_RTOL
+        else:
+            assert relerr(out["grad_logPhi"][k][rows], g["logPhi"][rows]) <= GRAD_RTOL
+        scale = max(abs(g["ell"]), abs(g["var"]), abs(g["likvar"]))
+        for j, nm in enumerate(("ell", "var", "likvar")):
+            assert abs(out["grad_hyp"][k, j] - g[nm]) <= GRAD_RTOL * max(abs(g[nm]), 1e-3 * scale), (nm, out["grad_hyp"][k, j], g[nm])
+        assert abs(out["grad_b"][k, 0] - g["b"]) <= GRAD_RTOL * max(abs(g["b"]), 1e-3 * scale)
+        gk = out["grad_logPhi"][k]
+        assert np.abs(gk.sum(axis=1)).max() <= 1e-9 * np.abs(gk).sum(axis=1).max()   # softmax gradient: zero row sums
+        del g
