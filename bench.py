@@ -82,11 +82,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": reasons}
 
 
-def fp64_peak():
-    """FP64 roofline denominator.  MEASURED_PEAKS.json (driver-written) carries only HBM and bf16, so the fp64 figure is
-    this repo's own measurement on the same pool (tools/microbench -> profiles/r01_fp64_peak.json, r01_lib_peaks.json)."""
-    out = {"dmma_tflops": 37.14, "cublas_dgemm_tflops": 35.44, "source": "profiles/r01_fp64_peak.json (DMMA m8n8k4 issue rate), "
-           "profiles/r01_lib_peaks.json (cuBLAS DGEMM 8192^3); MEASURED_PEAKS.json has no fp64 entry"}
+def fp64_peak(device_index=0, torch=None):
+    """FP64 roofline denominator.  MEASURED_PEAKS.json (driver-written) carries only HBM and bf16, so the fp64 figures are
+    measured HERE, in this run, before the timed region: tools/microbench/fp64_peak (compiled by __graft_entry__.build():
+    DFMA and DMMA m8n8k4 issue rates over all SMs) and a cuBLAS DGEMM 4096^3 through torch.matmul, with the SM clock sampled
+    while they run.  The committed round-1 figures are the fallback when the binary is missing."""
+    out = {"dmma_tflops": 37.14, "cublas_dgemm_tflops": 35.44, "measured_this_run": None,
+           "source": "fallback: profiles/r01_fp64_peak.json (DMMA m8n8k4 issue rate), profiles/r01_lib_peaks.json (cuBLAS DGEMM 8192^3); "
+                     "MEASURED_PEAKS.json has no fp64 entry"}
     try:
         with open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")) as f:
             out["dmma_tflops"] = float(json.load(f)["dmma_tflops_bps8"])
@@ -94,6 +97,43 @@ def fp64_peak():
             out["cublas_dgemm_tflops"] = float(json.load(f)["dgemm_8192_tflops"])
     except Exception:
         pass
+    exe = os.path.join(ROOT, "tools", "microbench", "fp64_peak")
+    if not os.path.exists(exe):
+        return out
+    try:
+        sampler = ClockSampler(device_index)
+        sampler.start()
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=vis[device_index] if device_index < len(vis) else str(device_index))
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+        mb = json.loads(res.stdout.strip().splitlines()[-1])
+        dgemm = None
+        if torch is not None:
+            a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+            b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+            torch.matmul(a, b)
+            best = 1e30
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            dgemm = 2.0 * 4096 ** 3 / (best * 1e-3) / 1e12
+            del a, b
+        clk = sampler.stop()
+        out["measured_this_run"] = {"dmma_tflops": mb["dmma_tflops_bps8"], "dfma_tflops": mb["dfma_tflops_bps8"],
+                                    "cublas_dgemm_4096_tflops": None if dgemm is None else round(dgemm, 2),
+                                    "sm_mhz": clk.get("sm_mhz"), "reasons": clk.get("reasons"),
+                                    "how": "tools/microbench/fp64_peak (mma.sync.m8n8k4.f64 / fma.rn.f64 issue rate, 8 CTAs of 256 threads per SM, "
+                                           "best of 5) and torch.matmul fp64 4096^3 (best of 5), run inside bench.py before the timed region"}
+        out["dmma_tflops"] = float(mb["dmma_tflops_bps8"])
+        if dgemm is not None:
+            out["cublas_dgemm_tflops"] = round(dgemm, 2)
+        out["source"] = "measured in this run (roofline.peak_measured_this_run)"
+    except Exception as ex:
+        out["measured_this_run"] = {"error": repr(ex)}
     return out
 
 
@@ -172,6 +212,10 @@ def run_ours(args):
         bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=dev)
     N, ips = args.cells, args.items
+    # fp64 peak of this GPU, measured before anything else is resident (rank-local; the line reports rank 0's)
+    peak_info = fp64_peak(local, torch)
+    if world > 1:
+        dist.barrier()
     eng = _lib.Engine(local)
     H = synth_host(N)
     d = {k: torch.as_tensor(H[k], device=dev).contiguous() for k in ("t", "prior", "Y")}
@@ -241,7 +285,7 @@ def run_ours(args):
     launch_ms = phase_ms[dom] / (args.steps * waves_per_step)
     items_per_launch = ips / waves_per_step
     achieved = fl[dom] * items_per_launch / (launch_ms * 1e-3) / 1e12
-    pk = fp64_peak()
+    pk = peak_info
     gemm_ms = sum(phase_ms[k] for k in fl)
     total_flops = sum(fl.values()) * ips * args.steps
     traffic = None   # dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (148-item launch)
@@ -255,7 +299,8 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 3), "peak": pk["dmma_tflops"], "unit": "TFLOP/s",
                 "frac": round(achieved / pk["dmma_tflops"], 4), "traffic": traffic,
                 "launch_ms": round(launch_ms, 3), "items_per_launch": items_per_launch,
-                "flops_per_item": fl[dom], "peak_source": pk["source"], "cublas_dgemm_tflops": pk["cublas_dgemm_tflops"],
+                "flops_per_item": fl[dom], "peak_source": pk["source"], "peak_measured_this_run": pk["measured_this_run"],
+                "cublas_dgemm_tflops": pk["cublas_dgemm_tflops"],
                 "whole_step_tflops": round(total_flops / (ms * 1e-3) / 1e12, 3),
                 "whole_step_frac": round(total_flops / (ms * 1e-3) / 1e12 / pk["dmma_tflops"], 4),
                 "phase_ms_per_step": {k: round(v / args.steps, 3) for k, v in phase_ms.items()},

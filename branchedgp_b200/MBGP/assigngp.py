@@ -322,10 +322,12 @@ class AssignGP:
             return mean[0], np.repeat(var[0][:, :, None], self.D, axis=2)
         return mean[0], np.repeat(var[0][:, None], self.D, axis=1)
 
-    # ------------------------------------------------------------------ sampling utilities (data generation, not on the bound's path)
+    # ------------------------------------------------------------------ sampling (MBGP/assigngp.py:741-835)
     def predict_f_samples(self, Xnew, num_samples: Optional[int] = 1, full_cov: bool = True, full_output_cov: bool = False):
-        """Samples of the posterior latent functions at Xnew, [S, N, D] (MBGP/assigngp.py:741-798).  The posterior
-        moments come from the CUDA predict kernel; drawing the samples is host-side numpy."""
+        """Samples of the posterior latent functions at Xnew, [S, N, D] (MBGP/assigngp.py:741-798).  Posterior moments from the
+        CUDA predict kernels; with ``full_cov`` the D Cholesky factorisations of cov_d + jitter I and the products with the
+        normal draws run batched on the GPU (bgp_gaussian_samples_host, one CTA per output).  The draws themselves come from
+        numpy's global generator in the reference's shapes ([S, N, D] / [D, N, S])."""
         if full_cov and full_output_cov:
             raise NotImplementedError("The combination of both `full_cov` and `full_output_cov` is not supported.")
         S = 1 if num_samples is None else num_samples
@@ -336,19 +338,21 @@ class AssignGP:
             samples = mean + np.sqrt(cov) * np.random.standard_normal((S, N, D))
         else:
             z = np.random.standard_normal((D, N, S))
-            covd = np.transpose(cov, (2, 0, 1)) + gpflow.default_jitter() * np.eye(N)[None]
-            chol = np.linalg.cholesky(covd)
-            samples = np.transpose(mean.T[..., None] + chol @ z, (2, 1, 0))
+            samples = self.engine.gaussian_samples(z, mean=np.ascontiguousarray(mean.T), cov=np.ascontiguousarray(np.transpose(cov, (2, 0, 1))),
+                                                   jitter=gpflow.default_jitter())
         return samples[0] if num_samples is None else samples
 
     def sample_prior(self, x_expanded: np.ndarray, num_samples: int = 1) -> np.ndarray:
         """Samples of (f, g, h) from the prior at x_expanded, [S, N, D], each output with its own branching point
-        (MBGP/assigngp.py:800-835).  Host-side numpy (used to generate synthetic data)."""
+        (MBGP/assigngp.py:800-835): covariance generation, Cholesky and the product with the draws run on the GPU, one CTA per
+        output (bgp_gaussian_samples_host with from_kernel = 1)."""
         x_expanded = np.asarray(x_expanded, dtype=np.float64)
         N, D, S = x_expanded.shape[0], self.Y.shape[1], num_samples
-        cov = np.stack([self.kernel.K(x_expanded, dim=d) for d in range(D)], axis=0)
-        chol = np.linalg.cholesky(cov + gpflow.default_jitter() * np.eye(N)[None])
-        return np.transpose(chol @ np.random.standard_normal((D, N, S)), (2, 1, 0))
+        z = np.random.standard_normal((D, N, S))
+        k = self.kernel
+        return self.engine.gaussian_samples(z, X=x_expanded, bv=np.asarray(k.Bv.numpy(), dtype=np.float64).ravel(),
+                                            ell=float(k.kern.lengthscales.numpy()), kvar=float(k.kern.variance.numpy()), kernel=k.kind,
+                                            noise=float(k.noise_level), jitter=gpflow.default_jitter())
 
     def predict_y(self, Xnew, full_cov=False):
         mean, var = self.predict_f(Xnew, full_cov=full_cov)

@@ -53,18 +53,20 @@ def SetXExpandedBranchingPoint(XExpanded, B):
 
 
 def predictBranchingModel(m, full_cov=False):
-    """Predictive mean / variance of the three functions on 100 test points each (VBHelperFunctions.py:141-167)."""
+    """Predictive mean / variance of the three functions on 100 test points each (VBHelperFunctions.py:141-167).  The reference
+    calls ``predict_f`` once per function, each call refactorising the model; here the 300 test inputs go through ONE posterior
+    evaluation (one pair of Cholesky factorisations on the GPU) and the result is cut into the reference's three lists."""
     pt = m.t
     B = np.asarray(m.kernel.kernels[0].Bv).flatten()
     lo, hi = np.min(pt), np.max(pt)
-    ttestl, mul, varl = [], [], []
-    for f in range(1, 4):
-        ttest = np.linspace(lo, B, 100) if f == 1 else np.linspace(B, hi, 100)
-        Xtest = np.hstack((ttest, ttest * 0 + f))
-        mu, var = m.predict_f(Xtest, full_cov=full_cov)
-        assert np.all(np.isfinite(mu)), "All elements should be finite but are " + str(mu)
-        assert np.all(np.isfinite(var)), "All elements should be finite but are " + str(var)
-        mul.append(mu)
-        varl.append(var)
-        ttestl.append(ttest)
+    ttestl = [np.linspace(lo, B, 100) if f == 1 else np.linspace(B, hi, 100) for f in range(1, 4)]
+    Xtest = np.vstack([np.hstack((tt, tt * 0 + f)) for f, tt in zip(range(1, 4), ttestl)])
+    mu, var = m.predict_f(Xtest, full_cov=full_cov)
+    assert np.all(np.isfinite(mu)), "All elements should be finite but are " + str(mu)
+    assert np.all(np.isfinite(var)), "All elements should be finite but are " + str(var)
+    mul = [mu[100 * f:100 * (f + 1)] for f in range(3)]
+    if full_cov:
+        varl = [var[100 * f:100 * (f + 1), 100 * f:100 * (f + 1)] for f in range(3)]
+    else:
+        varl = [var[100 * f:100 * (f + 1)] for f in range(3)]
     return ttestl, mul, varl

@@ -60,6 +60,10 @@ SIGNATURES = {
                                                ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
+    "bgp_gaussian_samples_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p]),
     "bgp_get_phi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_fit_default_options": (None, [ctypes.c_void_p]),
     "bgp_dense_fit_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 2 + [ctypes.c_int]
@@ -67,6 +71,7 @@ SIGNATURES = {
     "bgp_sparse_fit_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
                             + [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 11),
     "bgp_debug_gemm_timers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "bgp_debug_wide_timers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "bgp_debug_linesearch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double]),
     "bgp_debug_lbfgs_direction": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bgp_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -293,6 +298,36 @@ class Engine:
         return mean, var
 
     # ------------------------------------------------------------------ batched fitting (device-resident L-BFGS)
+    def gaussian_samples(self, z, mean=None, cov=None, X=None, bv=None, ell=1.0, kvar=1.0, kernel=KERNEL_SQEXP, noise=1e-6,
+                         jitter=1e-6):
+        """samples[S, n, batch] = mean + chol(cov_d + jitter I) z[d]  for every output d (bgp_gaussian_samples_host).
+        z [batch, n, S] standard normal draws; either cov [batch, n, n] or (X [n, 2], bv [batch]) for the prior covariance of
+        the branching kernel with one branching point per output."""
+        z = _f64(z)
+        batch, n, S = z.shape
+        from_kernel = cov is None
+        if from_kernel:
+            X = _f64(X)
+            bv = _f64(bv).reshape(batch)
+            assert X.shape == (n, 2)
+        else:
+            cov = _f64(cov)
+            assert cov.shape == (batch, n, n)
+        if mean is not None:
+            mean = _f64(mean)
+            assert mean.shape == (batch, n)
+        out = np.empty((S, n, batch))
+        status = np.empty(batch, dtype=np.int32)
+        rc = self._lib.bgp_gaussian_samples_host(self._h, batch, n, S, int(from_kernel), _ptr(X) if from_kernel else None,
+                                                 _ptr(bv) if from_kernel else None, float(ell), float(kvar), int(kernel), float(noise),
+                                                 None if from_kernel else _ptr(cov), _ptr(mean), float(jitter), _ptr(z), _ptr(out),
+                                                 _ptr(status))
+        self._check(rc, "bgp_gaussian_samples_host")
+        if (status != 0).any():
+            d = int(np.flatnonzero(status)[0])
+            raise CholeskyError(f"Cholesky decomposition was not successful for output {d} (status {int(status[d])})")
+        return out
+
     def fit_options(self, **kw):
         """bgp_fit_default_options with keyword overrides (maxiter, maxcor, maxls, maxfun, ftol, gtol, train_hyp, has_prior,
         prior_mean, prior_sd, max_slots)."""

@@ -59,6 +59,8 @@ SlotLayout slot_layout(const DenseDims& d) {
     L.lse = take(d.N);
     L.klrow = take((size_t)d.N * PHI_KLW);
     L.rowpart = take((size_t)d.N * phi_col_chunks(d.M));
+    L.ctrl_bytes = (size_t)dense_wide_ctrl_ints(d.nM) * 4;
+    L.ctrl = take((L.ctrl_bytes + 7) / 8);
     L.total = o;
     return L;
 }
@@ -78,6 +80,7 @@ int bgp_create(int device, bgp_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) return fail(h, BGP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CU(dense_init_kernels());
+    CU(dense_wide_init_kernels());
     CU(sparse_init_kernels());
     h->kernels_ready = true;
     return BGP_OK;
@@ -90,6 +93,7 @@ int bgp_destroy(bgp_handle* h) {
     for (cudaStream_t s_ : h->lane_streams) cudaStreamDestroy(s_);
     if (h->shared_ready) cudaEventDestroy(h->shared_ready);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->pred_buf) cudaFree(h->pred_buf);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
     if (h->fit_state) cudaFree(h->fit_state);
@@ -143,7 +147,7 @@ static int pick_slots(bgp_handle* h, int count, size_t slot_bytes) {
 int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, const int* item_gene, const double* b,
                      const double* prior, const double* hyp, int kernel_kind, int model, double kl_weight, const double* logPhi,
                      const double* KConst, int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status,
-                     char* base, int slots, cudaStream_t st, bool mark, int global_item0) {
+                     char* base, int slots, cudaStream_t st, bool mark, int global_item0, bool allow_wide) {
     const DenseDims d = make_dims(N, D);
     const SlotLayout SL = slot_layout(d);
     const size_t stride_d = SL.total / 8;   // slot stride in doubles (SL.total is a multiple of 256)
@@ -161,6 +165,11 @@ int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const dou
     P.SCR = (double*)(base + SL.SCR); P.KT = (double*)(base + SL.KT); P.vec = (double*)(base + SL.vec);
     P.status = status; P.elbo = elbo; P.grad_hyp = grad_hyp;
     P.slot_stride = (long long)stride_d;
+    P.ctrl = (int*)(base + SL.ctrl);
+    P.ctrl_stride = (long long)(SL.total / 4);
+    // Few items in flight: deal the macro tiles of every item to G CTAs (bgp_dense_wide.cu).  BGP_DENSE_WIDE=0 / 1 forces a path.
+    int wide_mode = h->wide_mode;
+    if (const char* e = getenv("BGP_DENSE_WIDE")) { if (e[0] == '0') wide_mode = 0; else if (e[0] == '1') wide_mode = 1; }
 
     PhiParams F;
     memset(&F, 0, sizeof(F));
@@ -189,24 +198,35 @@ int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const dou
         dense_launch_prep(P, F.Apart, F.vpart, F.klpart, Y, item_gene, n, st);   // k_prep (+ k_ktable unless KConst)
         if (KConst == nullptr) h->launches++;
         pm(1);
+        const bool wide = wide_mode == 1 || (wide_mode < 0 && allow_wide && 2 * n <= h->sm_count);
+        int G = h->sm_count / n;
+        if (G < 1) G = 1;
+        if (wide) CU(cudaMemset2DAsync(P.ctrl, SL.total, 0, SL.ctrl_bytes, (size_t)n, st));
         for (int phase = 1; phase <= 9 && phase <= last; ++phase) {
             const bool grad_phase = (phase == 5 || phase == 6 || phase == 7 || phase == 9);
             if (grad_phase && !want_grad) continue;
-            dense_launch_phase(P, n, phase, st);
+            if (!wide || !dense_launch_phase_wide(P, n, phase, G, st)) dense_launch_phase(P, n, phase, st);
             pm(phase + 1);
         }
         if (want_grad && last >= 9) {
             phi_launch_backward(F, n, st);
             pm(11);
         }
-        if (h->pred_T > 0) {   // predict_f on this wave's forward state, 128 test inputs per launch
+        if (h->pred_T > 0) {   // predict_f on this wave's forward state
             const size_t vstride = h->pred_full ? (size_t)h->pred_T * h->pred_T : (size_t)h->pred_T;
             const size_t g0 = (size_t)global_item0 + item0;
-            for (int s0 = 0; s0 < h->pred_T; s0 += MB) {
-                const int tc = (h->pred_T - s0 < MB) ? (h->pred_T - s0) : MB;
-                dense_launch_predict(P, n, h->pred_X + 2 * (size_t)s0, tc, h->pred_T, s0, h->pred_full,
-                                     h->pred_mean + g0 * h->pred_T * D, h->pred_var + g0 * vstride, st);
-                h->launches++;
+            if (h->pred_full && h->pred_T > MB) {   // full covariance over more than one 128-input chunk: tall matrices in pred_ext
+                const size_t per_item = dense_predict_cov_scratch_doubles(d, 1, h->pred_T) - d.Mp;
+                dense_launch_predict_fullcov(P, n, h->pred_X, h->pred_T, h->pred_mean + g0 * h->pred_T * D, h->pred_var + g0 * vstride,
+                                             h->pred_ext + g0 * per_item, h->pred_neg1, st);
+                h->launches += 2;
+            } else {
+                for (int s0 = 0; s0 < h->pred_T; s0 += MB) {   // 128 test inputs per launch
+                    const int tc = (h->pred_T - s0 < MB) ? (h->pred_T - s0) : MB;
+                    dense_launch_predict(P, n, h->pred_X + 2 * (size_t)s0, tc, h->pred_T, s0, h->pred_full,
+                                         h->pred_mean + g0 * h->pred_T * D, h->pred_var + g0 * vstride, st);
+                    h->launches++;
+                }
             }
         }
         CU(cudaGetLastError());
@@ -283,6 +303,8 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
     if (const char* e = getenv("BGP_HOST_CONC")) conc = atoi(e) > 0 ? atoi(e) : conc;
     int gs = sm_cap / conc;                              // items per group: conc groups never ask for more CTAs than there are SMs
     if (gs < 1) gs = 1;
+    const bool few = 2 * count <= h->sm_count;           // few items: one group, its macro tiles dealt to all SMs (bgp_dense_wide.cu)
+    if (few) gs = count;
     int ngroups = (count + gs - 1) / gs;
     int lanes = ngroups < 2 * conc ? ngroups : 2 * conc;
     if (const char* e = getenv("BGP_HOST_LANES")) { const int l_ = atoi(e); if (l_ > 0) lanes = l_ < ngroups ? l_ : ngroups; }
@@ -363,7 +385,7 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
         rc = dense_run(h, n, N, D, (double*)(s + o_t), (double*)(s + o_Y), (int*)(ls + l_gene), (double*)(ls + l_b), (double*)(s + o_prior),
                        (double*)(ls + l_hyp), kernel_kind, model, kl_weight, (double*)(ls + l_lp), KConst ? (double*)(s + o_K) : nullptr,
                        want_grad, (double*)(ls + l_elbo), (double*)(ls + l_gh), want_grad ? (double*)(ls + l_g) : nullptr,
-                       (int*)(ls + l_st), (char*)h->ws + (size_t)l * gs * SL.total, gs, st, false, i0);
+                       (int*)(ls + l_st), (char*)h->ws + (size_t)l * gs * SL.total, gs, st, false, i0, few);
         if (rc != BGP_OK) break;
         CU(cudaMemcpyAsync(pin_elbo + i0, ls + l_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(pin_st + i0, ls + l_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -531,16 +553,34 @@ int bgp_dense_predict_host(bgp_handle* h, int count, int N, int D, const double*
                            const double* logPhi, int T, const double* Xnew, int full_cov, double* mean, double* var) {
     if (!h) return BGP_ERR_ARG;
     if (T <= 0 || !Xnew || !mean || !var) return fail(h, BGP_ERR_ARG, "predict needs T > 0, Xnew, mean and var");
-    if (full_cov && T > MB) return fail(h, BGP_ERR_ARG, "full_cov is limited to %d test inputs per call", MB);
     CU(cudaSetDevice(h->device));
     const size_t vlen = full_cov ? (size_t)T * T : (size_t)T;
-    double *dX = nullptr, *dmean = nullptr, *dvar = nullptr, *delbo = nullptr;
-    int* dst = nullptr;
-    CU(cudaMalloc(&dX, (size_t)T * 16));
-    CU(cudaMalloc(&dmean, (size_t)count * T * D * 8));
-    CU(cudaMalloc(&dvar, (size_t)count * vlen * 8));
+    // one grow-only device buffer: test inputs, mean, variance and (full covariance over more than 128 inputs) the tall matrices
+    // of every item (the host entry below runs several item groups concurrently, so every item has its own)
+    const DenseDims dd = make_dims(N, D);
+    const bool tiled = full_cov && T > MB;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t o_X = take((size_t)T * 16), o_mean = take((size_t)count * T * D * 8), o_var = take((size_t)count * vlen * 8);
+    const size_t o_ext = take(tiled ? dense_predict_cov_scratch_doubles(dd, count, T) * 8 : 0);
+    if (h->pred_buf_bytes < o) {
+        if (h->pred_buf) cudaFree(h->pred_buf);
+        h->pred_buf = nullptr; h->pred_buf_bytes = 0;
+        cudaError_t e = cudaMalloc(&h->pred_buf, o);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(h, BGP_ERR_NOMEM, "predict buffers of %zu bytes: %s", o, cudaGetErrorString(e)); }
+        h->pred_buf_bytes = o;
+    }
+    char* pb = (char*)h->pred_buf;
+    double* dX = (double*)(pb + o_X); double* dmean = (double*)(pb + o_mean); double* dvar = (double*)(pb + o_var);
     CU(cudaMemcpy(dX, Xnew, (size_t)T * 16, cudaMemcpyHostToDevice));
     h->pred_X = dX; h->pred_T = T; h->pred_full = full_cov; h->pred_mean = dmean; h->pred_var = dvar;
+    h->pred_ext = tiled ? (double*)(pb + o_ext) : nullptr;
+    h->pred_neg1 = nullptr;
+    if (tiled) {
+        h->pred_neg1 = h->pred_ext + dense_predict_cov_scratch_doubles(dd, count, T) - dd.Mp;
+        dense_fill(h->pred_neg1, dd.Mp, -1.0, 0);
+        CU(cudaStreamSynchronize(0));
+    }
     const int saved = h->stop_phase;
     h->stop_phase = 4;
     std::vector<double> elbo(count);
@@ -548,7 +588,7 @@ int bgp_dense_predict_host(bgp_handle* h, int count, int N, int D, const double*
     int rc = bgp_dense_elbo_grad_host(h, count, N, D, t, Y, nY, item_gene, b, prior, hyp, kernel_kind, model, 1.0, logPhi, nullptr, 0,
                                       elbo.data(), nullptr, nullptr, status.data());
     h->stop_phase = saved;
-    h->pred_T = 0; h->pred_X = nullptr; h->pred_mean = nullptr; h->pred_var = nullptr;
+    h->pred_T = 0; h->pred_X = nullptr; h->pred_mean = nullptr; h->pred_var = nullptr; h->pred_ext = nullptr;
     if (rc == BGP_OK) {
         cudaError_t e1 = cudaMemcpy(mean, dmean, (size_t)count * T * D * 8, cudaMemcpyDeviceToHost);
         cudaError_t e2 = cudaMemcpy(var, dvar, (size_t)count * vlen * 8, cudaMemcpyDeviceToHost);
@@ -556,7 +596,6 @@ int bgp_dense_predict_host(bgp_handle* h, int count, int N, int D, const double*
         for (int i = 0; i < count && rc == BGP_OK; ++i)
             if (status[i] != 0) rc = fail(h, BGP_ERR_CUDA, "Cholesky decomposition was not successful for item %d (status %d)", i, status[i]);
     }
-    cudaFree(dX); cudaFree(dmean); cudaFree(dvar); (void)delbo; (void)dst;
     return rc;
 }
 
@@ -670,6 +709,14 @@ int bgp_debug_gemm_timers(bgp_handle* h, unsigned long long* out8, int reset) {
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
     dense_read_gemm_timers(out8, reset);
+    return BGP_OK;
+}
+
+int bgp_debug_wide_timers(bgp_handle* h, unsigned long long* out48, int reset) {
+    if (!h || !out48) return BGP_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    dense_read_wide_timers(out48, reset);
     return BGP_OK;
 }
 

@@ -13,33 +13,10 @@
 //   k_trmm    G = L Pbar (lower), Lbar = 2 Delta G + v zbar^T, delta = rowsum(G o L)
 //   k_post    Abar, vbar, d/d likvar, ELBO
 //   k_adj     gather form of the blocked Cholesky adjoint, fused with sum(Ktilde o dK/dtheta)
-#include "bgp_dense.cuh"
-#include "bgp_gemm.cuh"
+#include "bgp_dense_dev.cuh"
 #include "bgp_launch.h"
 
 namespace bgp {
-
-#define DENSE_SETUP()                                                                              \
-    extern __shared__ __align__(128) unsigned char smem[];                                         \
-    const int tid = threadIdx.x;                                                                   \
-    const int slot = P.slot_map ? P.slot_map[blockIdx.x] : (int)blockIdx.x;                        \
-    const int item = P.item0 + slot;                                                               \
-    const DenseDims& dm = P.d;                                                                     \
-    const VecLayout VL = vec_layout(dm.Mp, dm.nM, dm.D);                                           \
-    double* const vec = P.vec + (size_t)slot * P.slot_stride;                                       \
-    double* const LC = P.LC + (size_t)slot * P.slot_stride;                                         \
-    double* const RX = P.RX + (size_t)slot * P.slot_stride;                                         \
-    double* const PB = P.PB + (size_t)slot * P.slot_stride;                                         \
-    double* const LB = P.LB + (size_t)slot * P.slot_stride;                                         \
-    double* const LCe = P.LCe + (size_t)slot * P.slot_stride;                                 \
-    double* const LinvD = P.LinvD + (size_t)slot * P.slot_stride;                        \
-    double* const RinvD = P.RinvD + (size_t)slot * P.slot_stride;                        \
-    double* const SCR = P.SCR + (size_t)slot * P.slot_stride;                                \
-    const double ell = P.hyp[(size_t)item * 3 + 0];                                                \
-    const double kvar = P.hyp[(size_t)item * 3 + 1];                                               \
-    const double likvar = P.hyp[(size_t)item * 3 + 2];                                             \
-    (void)tid; (void)vec; (void)LC; (void)RX; (void)PB; (void)LB; (void)LCe; (void)LinvD; (void)RinvD; (void)SCR; \
-    (void)ell; (void)kvar; (void)likvar; (void)VL; (void)smem;
 
 // ------------------------------------------------------------------------------------------------ k_prep
 struct PrepArgs {
@@ -104,200 +81,6 @@ __global__ void __launch_bounds__(NTHREADS) k_ktable(DenseParams P) {
         KT[e] = k;
         KT[nn + e] = dl;
     }
-}
-
-// ------------------------------------------------------------------------------------------------ covariance
-// K[(t,f),(t',f')] for cell-major rows 3*cell + f  (VBHelperFunctions.py:170-194; branch_kernParamGPflow.py:117-198).
-__device__ __forceinline__ double kgen(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ KT, int gi,
-                                       int gj, double kinv) {
-    const int M = P.d.M;
-    if (gi >= M || gj >= M) return gi == gj ? 1.0 : 0.0;   // identity padding
-    if (P.KConst != nullptr) return P.KConst[(size_t)gi * M + gj];
-    const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
-    double k;
-    if (fi == fj) k = KT[(size_t)ci * P.d.N + cj];
-    else k = (ka[ci] * kinv) * ka[cj];
-    if (gi == gj) k += P.square_noise;
-    return k;
-}
-
-// ------------------------------------------------------------------------------------------------ 128x128 helpers in shared memory
-// The 128x128 diagonal macro blocks are factored and inverted in shared memory as 4x4 blocks of 32x32 tiles.  A 32x32 diagonal
-// tile is factored with its rows in the registers of ONE warp (lane = row, pivots and multipliers travel by shuffles) and
-// inverted by forward substitution (lane = column); every 32x32 tile product is split into four 8-row strips, so the sixteen
-// warps work on up to four tile products at a time.  About twenty CTA barriers per block instead of several hundred.
-// Scratch behind Dm (which occupies MB * DLD doubles of the ring): 4 inverse diagonal tiles + 3 product tiles, ld = TS + 1;
-// the six tiles of Dm above the diagonal serve as parking space for the off-diagonal tiles of the inverse.
-constexpr int TLD = TS + 1;
-constexpr int TSCR = TS * TLD;   // doubles per scratch tile
-
-// In-place lower Cholesky of the 32x32 tile T (leading dimension ld) by ONE warp: lane = row, left-looking (column j is formed
-// from the finished columns to its left, so the inner loop only loads; a fully unrolled register version ran out of instruction
-// cache).  One reciprocal square root per pivot instead of a square root and a division on the critical path.
-__device__ __forceinline__ void chol32_warp(double* T, int ld, int& fail, int base_index, int lane) {
-    double* row = T + lane * ld;
-    for (int j = 0; j < TS; ++j) {
-        const double* rj = T + j * ld;
-        double s0 = row[j], s1 = 0.0;
-        for (int k = 0; k + 1 < j; k += 2) {
-            s0 = fma(-row[k], rj[k], s0);
-            s1 = fma(-row[k + 1], rj[k + 1], s1);
-        }
-        if (j & 1) s0 = fma(-row[j - 1], rj[j - 1], s0);
-        const double a = s0 + s1;                          // A_ij - sum_k L_ik L_jk
-        double d = __shfl_sync(0xffffffffu, a, j);
-        if (!(d > 0.0)) {
-            if (fail == 0) fail = base_index + j + 1;
-            d = 1.0;
-        }
-        const double rinv = rsqrt(d);
-        __syncwarp();
-        if (lane >= j) row[j] = (lane == j) ? d * rinv : a * rinv;
-        __syncwarp();
-    }
-}
-
-// X = inverse of the lower-triangular 32x32 tile L (upper part of L ignored, upper part of X zeroed) by ONE warp: lane c solves
-// column c by forward substitution (it only re-reads what it wrote itself).
-__device__ __forceinline__ void trinv32_warp(const double* L, int ldl, double* X, int ldx, int lane) {
-    const double dinv = 1.0 / L[lane * ldl + lane];   // all 32 divisions in parallel
-    for (int i = 0; i < TS; ++i) {
-        const double* li = L + i * ldl;
-        double s0 = (lane == i) ? 1.0 : 0.0, s1 = 0.0;
-        for (int k = 0; k + 1 < i; k += 2) {
-            s0 = fma(-li[k], X[k * ldx + lane], s0);
-            s1 = fma(-li[k + 1], X[(k + 1) * ldx + lane], s1);
-        }
-        if (i & 1) s0 = fma(-li[i - 1], X[(i - 1) * ldx + lane], s0);
-        const double rii = __shfl_sync(0xffffffffu, dinv, i);
-        X[i * ldx + lane] = (lane <= i) ? (s0 + s1) * rii : 0.0;
-    }
-    __syncwarp();
-}
-
-// Rows r0 .. r0+7 of  C = c0 * C + alpha * A * op(B)  on 32x32 tiles, ONE warp: lane = column of C.  C may alias A (the strip of A
-// is read completely before the strip of C is written, and other warps own other strips).
-template <bool TB>
-__device__ __forceinline__ void tile_mm_strip(double* C, int ldc, double c0, double alpha, const double* A, int lda, const double* B,
-                                              int ldb, int r0, int lane) {
-    double acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < TS; ++k) {
-        const double b = TB ? B[lane * ldb + k] : B[k * ldb + lane];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fma(A[(r0 + i) * lda + k], b, acc[i]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        double* c = C + (r0 + i) * ldc + lane;
-        *c = (c0 == 0.0) ? alpha * acc[i] : c0 * *c + alpha * acc[i];
-    }
-}
-
-// In-place lower Cholesky of Dm (row-major, leading dimension DLD).  Non-positive pivots are replaced by 1 and reported.
-// Right-looking over 32-column panels.
-__device__ void chol128(double* Dm, int& fail, int base_index) {
-    __shared__ int fail_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, grp = warp >> 2;   // 8-row strip and tile-product slot of this warp
-    double* Winv = Dm + MB * DLD;               // inverse of the current diagonal tile
-    __syncthreads();
-    for (int p = 0; p < TPM; ++p) {
-        double* Tpp = Dm + (TS * p) * DLD + TS * p;
-        if (warp == 0) {
-            chol32_warp(Tpp, DLD, fail, base_index + TS * p, lane);
-            trinv32_warp(Tpp, DLD, Winv, TLD, lane);
-        }
-        __syncthreads();
-        // panel: L_ip = A_ip inv(L_pp)^T
-        if (grp < TPM - 1 - p) {
-            double* Aip = Dm + (TS * (p + 1 + grp)) * DLD + TS * p;
-            tile_mm_strip<true>(Aip, DLD, 0.0, 1.0, Aip, DLD, Winv, TLD, 8 * q, lane);
-        }
-        __syncthreads();
-        // trailing tiles (i, jt), p < jt <= i: A_ij -= L_ip L_jp^T  (at most six, four at a time)
-        {
-            int idx = 0;
-            for (int i = p + 1; i < TPM; ++i)
-                for (int jt = p + 1; jt <= i; ++jt, ++idx)
-                    if ((idx & 3) == grp)
-                        tile_mm_strip<true>(Dm + (TS * i) * DLD + TS * jt, DLD, 1.0, -1.0, Dm + (TS * i) * DLD + TS * p, DLD,
-                                            Dm + (TS * jt) * DLD + TS * p, DLD, 8 * q, lane);
-        }
-        __syncthreads();
-    }
-    // the pivot checks ran in warp 0 only: share its verdict
-    if (tid == 0) fail_s = fail;
-    __syncthreads();
-    fail = fail_s;
-    __syncthreads();
-}
-
-// In-place inverse of the lower-triangular Dm; the tiles above the diagonal are used as parking space.  With X_pp the inverted
-// diagonal tiles, the off-diagonal tiles follow by distance d = i - p from the diagonal:
-//     X_ip = -X_ii (L_ip X_pp + sum_{p < k < i} L_ik X_kp)
-// All of them are parked in the mirrored upper tiles (p, i), so the original L tiles stay readable until the final move.
-__device__ void trinv128(double* Dm) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, grp = warp >> 2;
-    double* Winv = Dm + MB * DLD;               // 4 inverse diagonal tiles
-    double* Sscr = Winv + TPM * TSCR;           // product tiles of the current distance
-    __syncthreads();
-    if (warp < TPM) trinv32_warp(Dm + (TS * warp) * DLD + TS * warp, DLD, Winv + warp * TSCR, TLD, lane);
-    __syncthreads();
-    for (int d = 1; d < TPM; ++d) {
-        const int ntile = TPM - d;   // tiles (p + d, p), p = 0 .. ntile-1: one group of four warps each
-        if (grp < ntile) {
-            const int p = grp, i = p + d;
-            double* S = Sscr + p * TSCR;
-            tile_mm_strip<false>(S, TLD, 0.0, 1.0, Dm + (TS * i) * DLD + TS * p, DLD, Winv + p * TSCR, TLD, 8 * q, lane);
-            for (int k = p + 1; k < i; ++k)   // X_kp is parked at (p, k)
-                tile_mm_strip<false>(S, TLD, 1.0, 1.0, Dm + (TS * i) * DLD + TS * k, DLD, Dm + (TS * p) * DLD + TS * k, DLD, 8 * q, lane);
-        }
-        __syncthreads();
-        if (grp < ntile) {
-            const int p = grp, i = p + d;
-            tile_mm_strip<false>(Dm + (TS * p) * DLD + TS * i, DLD, 0.0, -1.0, Winv + i * TSCR, TLD, Sscr + p * TSCR, TLD, 8 * q, lane);
-        }
-        __syncthreads();
-    }
-    // parked tiles (p, i) -> (i, p), and the diagonal tiles of the inverse (lower part)
-    for (int e = tid; e < 6 * TS * TS; e += GEMM_THREADS) {
-        const int t6 = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
-        const int ii = t6 < 1 ? 1 : (t6 < 3 ? 2 : 3);            // (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
-        const int pp = t6 < 1 ? 0 : (t6 < 3 ? t6 - 1 : t6 - 3);
-        Dm[(TS * ii + r) * DLD + TS * pp + c] = Dm[(TS * pp + r) * DLD + TS * ii + c];
-    }
-    for (int e = tid; e < TPM * TS * TS; e += GEMM_THREADS) {
-        const int pp = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
-        if (c <= r) Dm[(TS * pp + r) * DLD + TS * pp + c] = Winv[pp * TSCR + r * TLD + c];
-    }
-    __syncthreads();
-}
-
-// Lower tiles (a >= b) of the 128x128 smem block -> global tiles.  packed != nullptr: block-lower matrix position
-// (4J+a, 4J+b);  block != nullptr: 4x4 tile block.  Upper triangle of diagonal tiles is written as zero.
-// dalt (optional): diagonal tiles with `dadd` added on the diagonal.
-__device__ void store_lower_block(const double* Dm, int J, double* packed, double* block, double* dalt, double dadd) {
-    const int tid = threadIdx.x;
-    for (int a = 0; a < TPM; ++a)
-        for (int b = 0; b <= a; ++b) {
-            double* tp = packed ? packed + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS : nullptr;
-            double* tb = block ? block + (size_t)(a * TPM + b) * TILE_ELEMS : nullptr;
-            double* td = (dalt && a == b) ? dalt + (size_t)(TPM * J + a) * TILE_ELEMS : nullptr;
-            for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
-                const int i = e >> 5, j = e & 31;
-                double v = Dm[(TS * a + i) * DLD + TS * b + j];
-                if (a == b && j > i) v = 0.0;
-                const int o = tswz(i, j);
-                if (tp) tp[o] = v;
-                if (tb) tb[o] = v;
-                if (td) td[o] = v + ((i == j) ? dadd : 0.0);
-            }
-        }
 }
 
 // ------------------------------------------------------------------------------------------------ k_chol
@@ -726,27 +509,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_post(DenseParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_adj
-// sum over the stored lower triangle of Ktilde o dK/dtheta.  w carries 2*Kbar_ij off the diagonal and Kbar_ii on it.
-__device__ __forceinline__ void hyper_accum(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ dkal,
-                                            const double* __restrict__ dkab, const double* __restrict__ KT, int gi, int gj, double w,
-                                            double kvar, double kinv, double& gl, double& gv, double& gb) {
-    const int M = P.d.M;
-    if (gi >= M || gj >= M || gj > gi) return;
-    if (gi == gj) w *= 0.5;
-    const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
-    if (fi == fj) {
-        const size_t e = (size_t)ci * P.d.N + cj;
-        gl += w * KT[(size_t)P.d.N * P.d.N + e];
-        gv += w * KT[e] / kvar;
-    } else {
-        const double a = ka[ci], b = ka[cj];
-        const double cr = (a * kinv) * b;
-        gl += w * (dkal[ci] * b + a * dkal[cj]) * kinv;
-        gv += w * cr * (2.0 / kvar - kinv);
-        gb += w * (dkab[ci] * b + a * dkab[cj]) * kinv;
-    }
-}
-
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_adj(DenseParams P) {
     DENSE_SETUP();
     Pipe pipe;
@@ -876,6 +638,9 @@ struct PredictArgs {
     int par_chunks;       // grid.y = chunks of 128 test inputs, each with its own scratch inside PB / LB (T, s0 derived per chunk)
     double* mean;         // [slot][T][D]
     double* var;          // [slot][T] or [slot][T][T]
+    double* ext;          // optional scratch outside the slot for the tall matrices of every (slot, chunk): full covariance over more than 128 inputs
+    long long ext_chunk;  // doubles per (slot, chunk) in ext: two tall matrices + 32 scratch tiles
+    const double* neg1;   // Mp times -1.0 (k-scale of the subtracted Gram product in k_predict_cov)
 };
 
 __device__ __forceinline__ double kpair(const DenseParams& P, double t1, int f1, double t2, int f2, double ell, double kvar, double kinv,
@@ -898,10 +663,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
     const double b = P.bv[item];
     const double kinv = 1.0 / (kvar + JITTER);
     // scratch blocks: the slot's SCR, or (chunk-parallel) a private pair behind the tall matrices of all chunks in PB
-    double* S0 = Q.par_chunks ? PB + (size_t)gridDim.y * tall + (size_t)chunk * 32 * TILE_ELEMS : SCR;
+    double* const extc = Q.ext ? Q.ext + ((size_t)slot * gridDim.y + chunk) * Q.ext_chunk : nullptr;
+    double* S0 = extc ? extc + 2 * tall : (Q.par_chunks ? PB + (size_t)gridDim.y * tall + (size_t)chunk * 32 * TILE_ELEMS : SCR);
     double* S1 = S0 + 16 * TILE_ELEMS;
-    double* T1 = PB + (size_t)chunk * tall;   // tall tile matrices: tile (r, c) at (r*4 + c)
-    double* T2 = LB + (size_t)chunk * tall;
+    double* T1 = extc ? extc : PB + (size_t)chunk * tall;   // tall tile matrices: tile (r, c) at (r*4 + c)
+    double* T2 = extc ? extc + tall : LB + (size_t)chunk * tall;
     const Opnd opL = opnd_packed(LC, ACC_ROWK, LCe);
     const Opnd opR = opnd_packed(RX, ACC_ROWK);
     Acc acc;
@@ -1004,7 +770,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
             Q.var[(size_t)slot * Q.Ttot + qs0 + s] = r;
         }
     }
-    if (Q.full_cov) {
+    if (Q.full_cov && Q.ext == nullptr) {
         // cov = K(Xnew) + tmp2^T tmp2 - tmp1^T tmp1   (128 x 128 Gram matrices through the tile GEMM)
         const Opnd o2 = opnd_block(T2, ACC_COLK, 0, 0, 0), o1 = opnd_block(T1, ACC_COLK, 0, 0, 0);
         acc_zero(acc);
@@ -1031,9 +797,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict(DenseParams P, Pred
     }
 }
 
+// Full covariance over more than 128 test inputs: block (c1, c2), c1 >= c2, of  K(Xnew) + tmp2^T tmp2 - tmp1^T tmp1  from the tall
+// matrices k_predict left in the external scratch (one CTA per item and block pair; the subtraction rides on the k-scale).
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_predict_cov(DenseParams P, PredictArgs Q, int chunks) {
+    DENSE_SETUP();
+    Pipe pipe;
+    pipe_init(pipe, smem);
+    const int nT = dm.nT;
+    int c1 = 0;
+    while ((c1 + 1) * (c1 + 2) / 2 <= (int)blockIdx.y) ++c1;
+    const int c2 = (int)blockIdx.y - c1 * (c1 + 1) / 2;
+    const size_t tall = (size_t)nT * TPM * TILE_ELEMS;
+    const double* e1 = Q.ext + ((size_t)slot * chunks + c1) * Q.ext_chunk;
+    const double* e2 = Q.ext + ((size_t)slot * chunks + c2) * Q.ext_chunk;
+    const double* Xn = Q.Xnew + (size_t)slot * Q.xnew_stride;
+    const double b = P.bv[item];
+    const double kinv = 1.0 / (kvar + JITTER);
+    const int Tt = Q.Ttot;
+    Acc acc;
+    acc_zero(acc);
+    gemm_macro(acc, pipe, opnd_block(e1 + tall, ACC_COLK, 0, 0, 0), 0, opnd_block(e2 + tall, ACC_COLK, 0, 0, 0), 0, 0, nT, nullptr);
+    gemm_macro(acc, pipe, opnd_block(e1, ACC_COLK, 0, 0, 0), 0, opnd_block(e2, ACC_COLK, 0, 0, 0), 0, 0, nT, Q.neg1);
+    double* var = Q.var + (size_t)slot * Tt * Tt;
+    acc_foreach(acc, 0, 0, [&](int it, int jt, int i, int j, double v0, double v1) {
+        const int s = c1 * MB + it * TS + i, r = c2 * MB + jt * TS + j;
+        if (s >= Tt) return;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int rr = r + h2;
+            if (rr >= Tt) continue;
+            double k = kpair(P, Xn[2 * s], (int)Xn[2 * s + 1], Xn[2 * rr], (int)Xn[2 * rr + 1], ell, kvar, kinv, b);
+            if (s == rr) k += P.square_noise;
+            const double val = k + (h2 ? v1 : v0);
+            var[(size_t)s * Tt + rr] = val;
+            if (c1 != c2) var[(size_t)rr * Tt + s] = val;
+        }
+    });
+}
+
+__global__ void k_fill(double* p, long long n, double v) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) p[e] = v;
+}
+
+size_t dense_predict_cov_scratch_doubles(const DenseDims& d, int nitems, int Ttot) {
+    const int chunks = (Ttot + MB - 1) / MB;
+    const size_t per_chunk = (size_t)(2 * d.nT * TPM + 32) * TILE_ELEMS;
+    return (size_t)nitems * chunks * per_chunk + d.Mp;
+}
+
+// mean [item][Ttot][D] and the full covariance [item][Ttot][Ttot] for any number of test inputs, after phases 1-4
+void dense_fill(double* p, long long n, double v, cudaStream_t st) { k_fill<<<8, 256, 0, st>>>(p, n, v); }
+
+// `ext`: scratch of the first item of this launch (items are dense_predict_cov_scratch_doubles(d, 1, Ttot) - Mp doubles apart);
+// `neg1`: Mp times -1.0
+void dense_launch_predict_fullcov(const DenseParams& P, int nitems, const double* Xnew, int Ttot, double* mean, double* var, double* ext,
+                                  const double* neg1, cudaStream_t st) {
+    const int chunks = (Ttot + MB - 1) / MB;
+    const long long per_chunk = (long long)(2 * P.d.nT * TPM + 32) * TILE_ELEMS;
+    PredictArgs Q{Xnew, 0, Ttot, 0, 1, 0, 0, 1, mean, var, ext, per_chunk, neg1};
+    k_predict<<<dim3(nitems, chunks), GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
+    k_predict_cov<<<dim3(nitems, chunks * (chunks + 1) / 2), GEMM_THREADS, SMEM_BYTES, st>>>(P, Q, chunks);
+}
+
 void dense_launch_predict(const DenseParams& P, int nitems, const double* Xnew, int T, int Ttot, int s0, int full_cov, double* mean,
                           double* var, cudaStream_t st, int rx_inverse) {
-    PredictArgs Q{Xnew, T, Ttot, s0, full_cov, rx_inverse, 0, 0, mean, var};
+    PredictArgs Q{Xnew, T, Ttot, s0, full_cov, rx_inverse, 0, 0, mean, var, nullptr, 0, nullptr};
     k_predict<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
 }
 
@@ -1044,11 +872,11 @@ void dense_launch_predict_slots(const DenseParams& P, int nitems, const double* 
     const int chunks = (Ttot + MB - 1) / MB;
     const long long need = (long long)chunks * ((long long)P.d.nT * TPM + 32) * TILE_ELEMS;
     if (need <= P.d.mat_elems) {
-        PredictArgs Q{Xnew, 0, Ttot, 0, 0, 1, xnew_stride, 1, mean, var};
+        PredictArgs Q{Xnew, 0, Ttot, 0, 0, 1, xnew_stride, 1, mean, var, nullptr, 0, nullptr};
         k_predict<<<dim3(nitems, chunks), GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
     } else {
         for (int s0 = 0; s0 < Ttot; s0 += MB) {
-            PredictArgs Q{Xnew + 2 * (size_t)s0, (Ttot - s0 < MB) ? (Ttot - s0) : MB, Ttot, s0, 0, 1, xnew_stride, 0, mean, var};
+            PredictArgs Q{Xnew + 2 * (size_t)s0, (Ttot - s0 < MB) ? (Ttot - s0) : MB, Ttot, s0, 0, 1, xnew_stride, 0, mean, var, nullptr, 0, nullptr};
             k_predict<<<nitems, GEMM_THREADS, SMEM_BYTES, st>>>(P, Q);
         }
     }
@@ -1081,6 +909,7 @@ cudaError_t dense_init_kernels() {
     if ((e = set_smem((const void*)k_trmm)) != cudaSuccess) return e;
     if ((e = set_smem((const void*)k_adj)) != cudaSuccess) return e;
     if ((e = set_smem((const void*)k_predict)) != cudaSuccess) return e;
+    if ((e = set_smem((const void*)k_predict_cov)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -64,6 +64,8 @@ struct DenseParams {
     double* KT;               // [2][N][N] base-kernel table k(t_i - t_j) and its lengthscale derivative (same-function entries of K)
     double* vec;              // vector area, see vec_layout()
     int* status;              // [count]
+    int* ctrl;                // task queues / dependency counters of the multi-CTA pipeline (bgp_dense_wide.cu), zeroed per evaluation
+    long long ctrl_stride;    // ints between the control areas of consecutive slots
     // outputs (device)
     double* elbo;             // [count]
     double* grad_hyp;         // [count][4]  d/d ell, var, likvar, b

@@ -1,0 +1,246 @@
+// Device helpers shared by the one-CTA-per-item dense pipeline (bgp_dense.cu) and the multi-CTA pipeline (bgp_dense_wide.cu).
+#pragma once
+#include "bgp_dense.cuh"
+#include "bgp_gemm.cuh"
+
+namespace bgp {
+
+#define DENSE_SETUP() DENSE_SETUP_IDX(blockIdx.x)
+#define DENSE_SETUP_IDX(BIDX)                                                                      \
+    extern __shared__ __align__(128) unsigned char smem[];                                         \
+    const int tid = threadIdx.x;                                                                   \
+    const int slot = P.slot_map ? P.slot_map[(BIDX)] : (int)(BIDX);                            \
+    const int item = P.item0 + slot;                                                               \
+    const DenseDims& dm = P.d;                                                                     \
+    const VecLayout VL = vec_layout(dm.Mp, dm.nM, dm.D);                                           \
+    double* const vec = P.vec + (size_t)slot * P.slot_stride;                                       \
+    double* const LC = P.LC + (size_t)slot * P.slot_stride;                                         \
+    double* const RX = P.RX + (size_t)slot * P.slot_stride;                                         \
+    double* const PB = P.PB + (size_t)slot * P.slot_stride;                                         \
+    double* const LB = P.LB + (size_t)slot * P.slot_stride;                                         \
+    double* const LCe = P.LCe + (size_t)slot * P.slot_stride;                                 \
+    double* const LinvD = P.LinvD + (size_t)slot * P.slot_stride;                        \
+    double* const RinvD = P.RinvD + (size_t)slot * P.slot_stride;                        \
+    double* const SCR = P.SCR + (size_t)slot * P.slot_stride;                                \
+    const double ell = P.hyp[(size_t)item * 3 + 0];                                                \
+    const double kvar = P.hyp[(size_t)item * 3 + 1];                                               \
+    const double likvar = P.hyp[(size_t)item * 3 + 2];                                             \
+    (void)tid; (void)vec; (void)LC; (void)RX; (void)PB; (void)LB; (void)LCe; (void)LinvD; (void)RinvD; (void)SCR; \
+    (void)ell; (void)kvar; (void)likvar; (void)VL; (void)smem;
+
+// ------------------------------------------------------------------------------------------------ covariance
+// K[(t,f),(t',f')] for cell-major rows 3*cell + f  (VBHelperFunctions.py:170-194; branch_kernParamGPflow.py:117-198).
+__device__ __forceinline__ double kgen(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ KT, int gi,
+                                       int gj, double kinv) {
+    const int M = P.d.M;
+    if (gi >= M || gj >= M) return gi == gj ? 1.0 : 0.0;   // identity padding
+    if (P.KConst != nullptr) return P.KConst[(size_t)gi * M + gj];
+    const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
+    double k;
+    if (fi == fj) k = KT[(size_t)ci * P.d.N + cj];
+    else k = (ka[ci] * kinv) * ka[cj];
+    if (gi == gj) k += P.square_noise;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------ 128x128 helpers in shared memory
+// The 128x128 diagonal macro blocks are factored and inverted in shared memory as 4x4 blocks of 32x32 tiles.  A 32x32 diagonal
+// tile is factored with its rows in the registers of ONE warp (lane = row, pivots and multipliers travel by shuffles) and
+// inverted by forward substitution (lane = column); every 32x32 tile product is split into four 8-row strips, so the sixteen
+// warps work on up to four tile products at a time.  About twenty CTA barriers per block instead of several hundred.
+// Scratch behind Dm (which occupies MB * DLD doubles of the ring): 4 inverse diagonal tiles + 3 product tiles, ld = TS + 1;
+// the six tiles of Dm above the diagonal serve as parking space for the off-diagonal tiles of the inverse.
+constexpr int TLD = TS + 1;
+constexpr int TSCR = TS * TLD;   // doubles per scratch tile
+
+// In-place lower Cholesky of the 32x32 tile T (leading dimension ld) by ONE warp: lane = row, left-looking (column j is formed
+// from the finished columns to its left, so the inner loop only loads; a fully unrolled register version ran out of instruction
+// cache).  One reciprocal square root per pivot instead of a square root and a division on the critical path.
+__device__ __forceinline__ void chol32_warp(double* T, int ld, int& fail, int base_index, int lane) {
+    double* row = T + lane * ld;
+    for (int j = 0; j < TS; ++j) {
+        const double* rj = T + j * ld;
+        double s0 = row[j], s1 = 0.0;
+        for (int k = 0; k + 1 < j; k += 2) {
+            s0 = fma(-row[k], rj[k], s0);
+            s1 = fma(-row[k + 1], rj[k + 1], s1);
+        }
+        if (j & 1) s0 = fma(-row[j - 1], rj[j - 1], s0);
+        const double a = s0 + s1;                          // A_ij - sum_k L_ik L_jk
+        double d = __shfl_sync(0xffffffffu, a, j);
+        if (!(d > 0.0)) {
+            if (fail == 0) fail = base_index + j + 1;
+            d = 1.0;
+        }
+        const double rinv = rsqrt(d);
+        __syncwarp();
+        if (lane >= j) row[j] = (lane == j) ? d * rinv : a * rinv;
+        __syncwarp();
+    }
+}
+
+// X = inverse of the lower-triangular 32x32 tile L (upper part of L ignored, upper part of X zeroed) by ONE warp: lane c solves
+// column c by forward substitution (it only re-reads what it wrote itself).
+__device__ __forceinline__ void trinv32_warp(const double* L, int ldl, double* X, int ldx, int lane) {
+    const double dinv = 1.0 / L[lane * ldl + lane];   // all 32 divisions in parallel
+    for (int i = 0; i < TS; ++i) {
+        const double* li = L + i * ldl;
+        double s0 = (lane == i) ? 1.0 : 0.0, s1 = 0.0;
+        for (int k = 0; k + 1 < i; k += 2) {
+            s0 = fma(-li[k], X[k * ldx + lane], s0);
+            s1 = fma(-li[k + 1], X[(k + 1) * ldx + lane], s1);
+        }
+        if (i & 1) s0 = fma(-li[i - 1], X[(i - 1) * ldx + lane], s0);
+        const double rii = __shfl_sync(0xffffffffu, dinv, i);
+        X[i * ldx + lane] = (lane <= i) ? (s0 + s1) * rii : 0.0;
+    }
+    __syncwarp();
+}
+
+// Rows r0 .. r0+7 of  C = c0 * C + alpha * A * op(B)  on 32x32 tiles, ONE warp: lane = column of C.  C may alias A (the strip of A
+// is read completely before the strip of C is written, and other warps own other strips).
+template <bool TB>
+__device__ __forceinline__ void tile_mm_strip(double* C, int ldc, double c0, double alpha, const double* A, int lda, const double* B,
+                                              int ldb, int r0, int lane) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < TS; ++k) {
+        const double b = TB ? B[lane * ldb + k] : B[k * ldb + lane];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fma(A[(r0 + i) * lda + k], b, acc[i]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double* c = C + (r0 + i) * ldc + lane;
+        *c = (c0 == 0.0) ? alpha * acc[i] : c0 * *c + alpha * acc[i];
+    }
+}
+
+// In-place lower Cholesky of Dm (row-major, leading dimension DLD).  Non-positive pivots are replaced by 1 and reported.
+// Right-looking over 32-column panels.
+static __device__ void chol128(double* Dm, int& fail, int base_index) {
+    __shared__ int fail_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, grp = warp >> 2;   // 8-row strip and tile-product slot of this warp
+    double* Winv = Dm + MB * DLD;               // inverse of the current diagonal tile
+    __syncthreads();
+    for (int p = 0; p < TPM; ++p) {
+        double* Tpp = Dm + (TS * p) * DLD + TS * p;
+        if (warp == 0) {
+            chol32_warp(Tpp, DLD, fail, base_index + TS * p, lane);
+            trinv32_warp(Tpp, DLD, Winv, TLD, lane);
+        }
+        __syncthreads();
+        // panel: L_ip = A_ip inv(L_pp)^T
+        if (grp < TPM - 1 - p) {
+            double* Aip = Dm + (TS * (p + 1 + grp)) * DLD + TS * p;
+            tile_mm_strip<true>(Aip, DLD, 0.0, 1.0, Aip, DLD, Winv, TLD, 8 * q, lane);
+        }
+        __syncthreads();
+        // trailing tiles (i, jt), p < jt <= i: A_ij -= L_ip L_jp^T  (at most six, four at a time)
+        {
+            int idx = 0;
+            for (int i = p + 1; i < TPM; ++i)
+                for (int jt = p + 1; jt <= i; ++jt, ++idx)
+                    if ((idx & 3) == grp)
+                        tile_mm_strip<true>(Dm + (TS * i) * DLD + TS * jt, DLD, 1.0, -1.0, Dm + (TS * i) * DLD + TS * p, DLD,
+                                            Dm + (TS * jt) * DLD + TS * p, DLD, 8 * q, lane);
+        }
+        __syncthreads();
+    }
+    // the pivot checks ran in warp 0 only: share its verdict
+    if (tid == 0) fail_s = fail;
+    __syncthreads();
+    fail = fail_s;
+    __syncthreads();
+}
+
+// In-place inverse of the lower-triangular Dm; the tiles above the diagonal are used as parking space.  With X_pp the inverted
+// diagonal tiles, the off-diagonal tiles follow by distance d = i - p from the diagonal:
+//     X_ip = -X_ii (L_ip X_pp + sum_{p < k < i} L_ik X_kp)
+// All of them are parked in the mirrored upper tiles (p, i), so the original L tiles stay readable until the final move.
+static __device__ void trinv128(double* Dm) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, grp = warp >> 2;
+    double* Winv = Dm + MB * DLD;               // 4 inverse diagonal tiles
+    double* Sscr = Winv + TPM * TSCR;           // product tiles of the current distance
+    __syncthreads();
+    if (warp < TPM) trinv32_warp(Dm + (TS * warp) * DLD + TS * warp, DLD, Winv + warp * TSCR, TLD, lane);
+    __syncthreads();
+    for (int d = 1; d < TPM; ++d) {
+        const int ntile = TPM - d;   // tiles (p + d, p), p = 0 .. ntile-1: one group of four warps each
+        if (grp < ntile) {
+            const int p = grp, i = p + d;
+            double* S = Sscr + p * TSCR;
+            tile_mm_strip<false>(S, TLD, 0.0, 1.0, Dm + (TS * i) * DLD + TS * p, DLD, Winv + p * TSCR, TLD, 8 * q, lane);
+            for (int k = p + 1; k < i; ++k)   // X_kp is parked at (p, k)
+                tile_mm_strip<false>(S, TLD, 1.0, 1.0, Dm + (TS * i) * DLD + TS * k, DLD, Dm + (TS * p) * DLD + TS * k, DLD, 8 * q, lane);
+        }
+        __syncthreads();
+        if (grp < ntile) {
+            const int p = grp, i = p + d;
+            tile_mm_strip<false>(Dm + (TS * p) * DLD + TS * i, DLD, 0.0, -1.0, Winv + i * TSCR, TLD, Sscr + p * TSCR, TLD, 8 * q, lane);
+        }
+        __syncthreads();
+    }
+    // parked tiles (p, i) -> (i, p), and the diagonal tiles of the inverse (lower part)
+    for (int e = tid; e < 6 * TS * TS; e += GEMM_THREADS) {
+        const int t6 = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
+        const int ii = t6 < 1 ? 1 : (t6 < 3 ? 2 : 3);            // (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+        const int pp = t6 < 1 ? 0 : (t6 < 3 ? t6 - 1 : t6 - 3);
+        Dm[(TS * ii + r) * DLD + TS * pp + c] = Dm[(TS * pp + r) * DLD + TS * ii + c];
+    }
+    for (int e = tid; e < TPM * TS * TS; e += GEMM_THREADS) {
+        const int pp = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
+        if (c <= r) Dm[(TS * pp + r) * DLD + TS * pp + c] = Winv[pp * TSCR + r * TLD + c];
+    }
+    __syncthreads();
+}
+
+// Lower tiles (a >= b) of the 128x128 smem block -> global tiles.  packed != nullptr: block-lower matrix position
+// (4J+a, 4J+b);  block != nullptr: 4x4 tile block.  Upper triangle of diagonal tiles is written as zero.
+// dalt (optional): diagonal tiles with `dadd` added on the diagonal.
+static __device__ void store_lower_block(const double* Dm, int J, double* packed, double* block, double* dalt, double dadd) {
+    const int tid = threadIdx.x;
+    for (int a = 0; a < TPM; ++a)
+        for (int b = 0; b <= a; ++b) {
+            double* tp = packed ? packed + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS : nullptr;
+            double* tb = block ? block + (size_t)(a * TPM + b) * TILE_ELEMS : nullptr;
+            double* td = (dalt && a == b) ? dalt + (size_t)(TPM * J + a) * TILE_ELEMS : nullptr;
+            for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
+                const int i = e >> 5, j = e & 31;
+                double v = Dm[(TS * a + i) * DLD + TS * b + j];
+                if (a == b && j > i) v = 0.0;
+                const int o = tswz(i, j);
+                if (tp) tp[o] = v;
+                if (tb) tb[o] = v;
+                if (td) td[o] = v + ((i == j) ? dadd : 0.0);
+            }
+        }
+}
+
+// sum over the stored lower triangle of Ktilde o dK/dtheta.  w carries 2*Kbar_ij off the diagonal and Kbar_ii on it.
+__device__ __forceinline__ void hyper_accum(const DenseParams& P, const double* __restrict__ ka, const double* __restrict__ dkal,
+                                            const double* __restrict__ dkab, const double* __restrict__ KT, int gi, int gj, double w,
+                                            double kvar, double kinv, double& gl, double& gv, double& gb) {
+    const int M = P.d.M;
+    if (gi >= M || gj >= M || gj > gi) return;
+    if (gi == gj) w *= 0.5;
+    const int ci = gi / 3, fi = gi - 3 * ci, cj = gj / 3, fj = gj - 3 * cj;
+    if (fi == fj) {
+        const size_t e = (size_t)ci * P.d.N + cj;
+        gl += w * KT[(size_t)P.d.N * P.d.N + e];
+        gv += w * KT[e] / kvar;
+    } else {
+        const double a = ka[ci], b = ka[cj];
+        const double cr = (a * kinv) * b;
+        gl += w * (dkal[ci] * b + a * dkal[cj]) * kinv;
+        gv += w * cr * (2.0 / kvar - kinv);
+        gb += w * (dkab[ci] * b + a * dkab[cj]) * kinv;
+    }
+}
+
+}  // namespace bgp

@@ -14,6 +14,7 @@ struct bgp_handle {
     int sm_count = 0;
     int max_slots = 0;         // 0 = default
     int stop_phase = 0;
+    int wide_mode = -1;        // multi-CTA-per-item dense pipeline: -1 automatic (few items in flight), 0 never, 1 always
     char err[512] = {0};
     // workspace (grow-only)
     void* ws = nullptr;
@@ -42,6 +43,8 @@ struct bgp_handle {
     int ev_used = 0;
     // set by bgp_dense_predict_host around a forward-only dense call
     const double* pred_X = nullptr; int pred_T = 0; int pred_full = 0; double* pred_mean = nullptr; double* pred_var = nullptr;
+    void* pred_buf = nullptr; size_t pred_buf_bytes = 0;   // predict_f: test inputs, outputs and the full-covariance scratch (grow-only)
+    double* pred_ext = nullptr; double* pred_neg1 = nullptr;   // parts of pred_buf: tall matrices of the tiled full covariance, Mp x -1.0
     double prof_ms[BGP_NPHASES] = {0};
     long long launches = 0;
 };
@@ -59,7 +62,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 bgp::DenseDims make_dims(int N, int D);
 
 struct SlotLayout {   // byte offsets inside one slot
-    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, klrow, rowpart, total;
+    size_t LC, RX, PB, LB, LCe, LinvD, RinvD, SCR, KT, vec, Apart, vpart, klpart, lse, klrow, rowpart, ctrl, ctrl_bytes, total;
 };
 SlotLayout slot_layout(const bgp::DenseDims& d);
 int ensure_ws(bgp_handle* h, size_t bytes);
@@ -69,4 +72,4 @@ int ensure_stage(bgp_handle* h, size_t bytes);
 int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const double* Y, const int* item_gene, const double* b,
               const double* prior, const double* hyp, int kernel_kind, int model, double kl_weight, const double* logPhi,
               const double* KConst, int want_grad, double* elbo, double* grad_hyp, double* grad_logPhi, int* status,
-              char* base, int slots, cudaStream_t st, bool mark, int global_item0);
+              char* base, int slots, cudaStream_t st, bool mark, int global_item0, bool allow_wide = true);

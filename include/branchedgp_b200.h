@@ -161,6 +161,19 @@ int bgp_sparse_fit_host(bgp_handle* h, int count, int N, int D, int Mz, const do
                         double* hyp, double* phi, double* pred_mean, double* pred_var, int* iters, int* nfev, int* status,
                         double* logPhi_out);
 
+/* Batched Gaussian sampling: MBGP AssignGP.sample_prior (MBGP/assigngp.py:800-835) and the correlated branch of
+ * predict_f_samples (MBGP/assigngp.py:741-798).  For every output d = 0 .. batch-1:
+ *     C_d = cov_d + jitter I,   L_d = chol(C_d),   samples[s][i][d] = mean[d][i] + sum_j L_d[i][j] z[d][j][s]
+ * from_kernel = 1: cov_d = BranchKernelParam.K(X, dim=d) (MBGP/assigngp.py:103-187) built on the device from X[n][2]
+ *                  (time, function 1..3), the branching point bv[d], the base kernel (kernel_kind, ell, kvar) and `noise`
+ *                  (noise_level) on the diagonal;   from_kernel = 0: cov[batch][n][n] is given (posterior covariance).
+ * mean[batch][n] may be NULL (zero mean).  z[batch][n][S] are standard normal draws supplied by the caller (the reference draws
+ * tf.random.normal([D, N, S])), samples is [S][n][batch] like the reference's return value.  status[d] != 0: non-positive pivot.
+ * All pointers are HOST pointers. */
+int bgp_gaussian_samples_host(bgp_handle* h, int batch, int n, int S, int from_kernel, const double* X, const double* bv,
+                              double ell, double kvar, int kernel_kind, double noise, const double* cov, const double* mean,
+                              double jitter, const double* z, double* samples, int* status);
+
 /* Per-kernel device timing (CUDA events recorded on the caller's stream around every launch).  Phase ids:
  * 0 phi forward, 1 prep, 2 chol K, 3 P = L^T D L + I, 4 chol P, 5 solves, 6 trtri, 7 lauum, 8 trmm, 9 post, 10 adjoint,
  * 11 phi backward.  bgp_profile_read waits for the recorded events, accumulates milliseconds per phase since the last
@@ -184,6 +197,8 @@ int bgp_debug_dense_vector(bgp_handle* h, int slot, int which, double* out_host)
  * [0] cycles a consumer warp waited for the first stages of a GEMM call, [1] for later stages, [2] producer waits for a free
  * stage, [3] cycles inside the GEMM calls, [4] calls, [5] k-steps; summed over CTAs. */
 int bgp_debug_gemm_timers(bgp_handle* h, unsigned long long* out8, int reset);
+/* Same for the task sections of the multi-CTA dense pipeline (bgp_dense_wide.cu): 48 counters, zeros unless BGP_TIMING. */
+int bgp_debug_wide_timers(bgp_handle* h, unsigned long long* out48, int reset);
 
 /* Host-only hooks for the optimiser pieces of bgp_fit.cu (no GPU needed): one More'-Thuente line-search call on caller-owned
  * state[32] (returns 0 evaluate at *stp, 1 convergence, 2 warning, 3 error), and the limited-memory direction d = -H g

@@ -15,6 +15,14 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "dense_golden.n
 ELBO_RTOL, GRAD_RTOL = 1e-8, 1e-6
 
 
+@pytest.fixture(autouse=True, params=["one CTA per item", "many CTAs per item"])
+def dense_path(request, monkeypatch):
+    """Every test of this file runs on both dense pipelines: bgp_dense.cu (one CTA per work item, what batches of >= 74 items
+    take) and bgp_dense_wide.cu (the macro tiles of an item dealt to many CTAs, what few items in flight take)."""
+    monkeypatch.setenv("BGP_DENSE_WIDE", "0" if request.param == "one CTA per item" else "1")
+    return request.param
+
+
 def _pz(pr, b):
     return host_ref.prior_with_trunk_bgp(host_ref.expand_prior_bgp(pr["prior"]), b, pr["t"])
 

@@ -14,7 +14,8 @@ def _xnew(T, seed=0):
     return np.stack([np.sort(rng.uniform(0, 1, T)), rng.integers(1, 4, T).astype(float)], 1)
 
 
-@pytest.mark.parametrize("N,D,T,full", [(20, 1, 100, False), (50, 2, 150, False), (90, 1, 300, False), (45, 1, 60, True)])
+@pytest.mark.parametrize("N,D,T,full", [(20, 1, 100, False), (50, 2, 150, False), (90, 1, 300, False), (45, 1, 60, True),
+                                        (45, 1, 150, True), (30, 2, 300, True), (100, 1, 257, True)])
 def test_dense_predict_matches_oracle(engine, N, D, T, full):
     pr = make_problem(N, D=D, seed=300 + N)
     Xn = _xnew(T)
