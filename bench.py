@@ -198,6 +198,132 @@ def bind_to_gpu_numa_node(gpu_index):
         print(f"[bench] no NUMA binding for GPU {gpu_index}: {ex}", file=sys.stderr)
 
 
+
+def c5_side(eng, torch, dist, world, rank, dev, stream, peak_info, N=2000, items=148):
+    """One step of 148 items per GPU at the C5 shape, device-resident inputs; returns the side line."""
+    H5 = synth_host(N, seed=5)
+    d5 = {k: torch.as_tensor(H5[k], device=dev).contiguous() for k in ("t", "prior", "Y")}
+    first = rank * items
+    idx, gene, bb = item_arrays(first, items)
+    logPhi = init_logphi_device(torch, dev, N, H5["phi0"], H5["t"], bb, seed=77 + rank)
+    grad = torch.empty_like(logPhi)
+    elbo = torch.empty(items, dtype=torch.float64, device=dev)
+    gh = torch.zeros(items, 4, dtype=torch.float64, device=dev)
+    status = torch.zeros(items, dtype=torch.int32, device=dev)
+    gene_d, b_d = torch.as_tensor(gene, device=dev), torch.as_tensor(bb, device=dev)
+    hyp_d = torch.as_tensor(H5["hyp"][idx], device=dev).contiguous()
+    res_local = torch.empty(items, 5, dtype=torch.float64, device=dev)
+    res_all = torch.empty(world * items, 5, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        eng.dense_elbo_grad_device(items, N, 1, d5["t"].data_ptr(), d5["Y"].data_ptr(), N_GENES, gene_d.data_ptr(), b_d.data_ptr(),
+                                   d5["prior"].data_ptr(), hyp_d.data_ptr(), logPhi.data_ptr(), elbo.data_ptr(), gh.data_ptr(),
+                                   grad.data_ptr(), status.data_ptr(), stream=stream)
+        if world > 1:
+            res_local[:, 0] = elbo
+            res_local[:, 1:] = gh
+            dist.all_gather_into_tensor(res_all, res_local)
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    torch.cuda.synchronize()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    flops = 3.0 * float(3 * N) ** 3 * items * world
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"config": f"C5 shape: N={N} cells (M={3 * N}), {items} (gene, branching point) items per GPU, 1 warm-up + 1 timed step",
+            "value": round(world * items / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world, "ms_per_step": round(ms, 2),
+            "tflops_total": round(tf, 2), "frac_dmma_peak_per_gpu": round(tf / world / peak_info["dmma_tflops"], 4),
+            "status_nonzero": int((status != 0).sum().item()),
+            "genome_wide_sweep_minutes": round(20000 * 40 / (world * items / (ms * 1e-3)) / 60.0, 1)}
+
+
+def single_gene_fitmodel(eng, H, N=1000, grid=(0.3, 0.6, 1.1), maxiter=5):
+    """The reference's own call pattern at the headline size: FitModel on ONE gene (dense model, M = 0), one bound + gradient
+    evaluation at a time -- every evaluation has the whole GPU (multi-CTA-per-item pipeline, bgp_dense_wide.cu)."""
+    from branchedgp_b200 import FitBranchingModel
+    t, labels = H["t"], H["labels"].astype(float)
+    Y = H["Y"][3]                                  # [N, 1]
+    out = {"config": f"FitModel(M=0), 1 gene, N={N}, {len(grid)} grid points, maxiter={maxiter}, trainable hyper-parameters, fPredict=True"}
+    for name, kw in (("FitModel_scipy_driver", {}), ("FitModel_device_optimiser", {"optimizer": "device"})):
+        t0 = time.perf_counter()
+        r = FitBranchingModel.FitModel(list(grid), t, Y, labels, M=0, maxiter=maxiter, **kw)
+        out[name] = {"seconds": round(time.perf_counter() - t0, 3), "argmax_b": float(grid[int(np.argmax(r["loglik"]))])}
+    # latency of one evaluation through the host-array entry (what the SciPy driver pays per function evaluation)
+    from branchedgp_b200 import _lib
+    lp = _lib.pinned_empty((1, N, 3 * N))
+    lp[:] = -9.0
+    gp = _lib.pinned_empty((1, N, 3 * N))
+    args = (t, Y[None], np.zeros(1, dtype=np.int32), np.array([0.5]), H["prior"], np.array([[2.0, 3.0, 0.1]]), lp)
+    eng.dense_elbo_grad(*args, grad_out=gp)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.dense_elbo_grad(*args, grad_out=gp)
+    out["one_evaluation_ms_host_arrays_pinned"] = round((time.perf_counter() - t0) / 5 * 1e3, 2)
+    return out
+
+
+def hematopoiesis_recipe():
+    """The reference's own timed recipe (notebooks/Hematopoiesis.py:107-118: genes MPO and CTSG, every 20th of 3854 cells = 193
+    cells, 6 candidate branching points, FitModel defaults M = 10 inducing points, maxiter = 100, fPredict) on the committed
+    sub-sample (tests/golden/hematopoiesis_subsample.npz), wall seconds beside the notebook's stored 58.0 s / 64.9 s."""
+    from branchedgp_b200 import FitBranchingModel
+    z = np.load(os.path.join(ROOT, "tests", "golden", "hematopoiesis_subsample.npz"))
+    grid = [float(x) for x in z["Bsearch"]]
+    GPt, labels = z["GPt"], z["globalBranching"]
+    out = {"config": "notebooks/Hematopoiesis.py FitGene(g, ns=20): N=193 cells, 6 grid points, M=10, maxiter=100",
+           "reference_notebook_seconds": {"MPO": 58.0, "CTSG": 64.9, "hardware": "unnamed CPU (notebooks/Hematopoiesis.ipynb:435,498)"}}
+    FitBranchingModel.FitModel(grid[:2], GPt, z["GPy_MPO"], labels, maxiter=2)   # warm-up (library workspace)
+    for g in ("MPO", "CTSG"):
+        t0 = time.perf_counter()
+        r = FitBranchingModel.FitModel(grid, GPt, z["GPy_" + g], labels)
+        out[g] = {"FitModel_seconds": round(time.perf_counter() - t0, 3), "argmax_b": grid[int(np.argmax(r["loglik"]))]}
+    GPY = np.hstack([z["GPy_MPO"], z["GPy_CTSG"]])
+    t0 = time.perf_counter()
+    rb = FitBranchingModel.FitModelBatch(grid, GPt, GPY, labels)
+    out["FitModelBatch_both_genes_seconds"] = round(time.perf_counter() - t0, 3)
+    out["FitModelBatch_argmax_b"] = [grid[int(np.argmax(r["loglik"]))] for r in rb]
+    return out
+
+
+def pcie_probe(torch, dist, world, dev, mb=1024):
+    """H2D and D2H bandwidth of this rank's GPU from pinned memory while every rank copies at the same time (GB/s; min / mean
+    over ranks).  The e2e leg moves 24 MB per item each way, so on a multi-GPU box it is bounded by what the host's memory system and
+    PCIe root complexes deliver to all GPUs at once, not by one link."""
+    n = mb * (1 << 20) // 8
+    hbuf = torch.empty(n, dtype=torch.float64).pin_memory()
+    dbuf = torch.empty(n, dtype=torch.float64, device=dev)
+    res = []
+    for src, dst in ((hbuf, dbuf), (dbuf, hbuf)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        res.append(3 * n * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    tt = torch.tensor(res, dtype=torch.float64, device=dev)
+    lo, mean = tt.clone(), tt.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+        mean /= world
+    return {"h2d_GBps_min": round(float(lo[0]), 1), "h2d_GBps_mean": round(float(mean[0]), 1), "d2h_GBps_min": round(float(lo[1]), 1),
+            "d2h_GBps_mean": round(float(mean[1]), 1), "how": f"{mb} MiB pinned copies, all {world} rank(s) at the same time, one direction at a time"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -342,6 +468,11 @@ def run_ours(args):
                "api": "bgp_dense_elbo_grad_host (ctypes, pinned host buffers)", "timer": "host wall clock around the call, max over ranks",
                "elbo_checksum": float(out["elbo"].sum())}
         eng._lib.bgp_host_free(gptr)
+        del h_lp
+        try:
+            e2e["pcie_under_load"] = pcie_probe(torch, dist, world, dev)
+        except Exception as exc:
+            e2e["pcie_under_load"] = {"error": repr(exc)}
 
     # ---- the same evaluations inside the device-resident batched L-BFGS (bgp_dense_fit_host): a few iterations of one wave
     fit = None
@@ -365,22 +496,38 @@ def run_ours(args):
                "evals_per_s": round(float(nev.item()) / float(tf.item()), 2), "status_counts": np.bincount(fo["status"], minlength=6).tolist(),
                "note": "wall clock of the whole call incl. allocation of the optimiser state and the final Phi / prediction outputs"}
 
-    # ---- the inducing-point configurations of BASELINE.json (C3 sparse BGP, C4 MBGP), device-resident inputs, N = 1 only:
-    # parity-test cases, reported beside the headline so that their roofline figures come from the same run
+    # ---- side measurements.  The engine of the headline measurement is closed first (it gives back the dense workspace and the
+    # optimiser state of the fit, 116 GB).
+    del keep
+    eng.close()
+    torch.cuda.empty_cache()
+    eng = _lib.Engine(local)
+
+    # C5 shape (BASELINE.json configs[4]: N = 2000 cells, genome-wide sweep sharded over the GPUs): one wave of 148 items per GPU,
+    # timed like the headline (device-resident inputs, CUDA events, max over ranks, NCCL gather of the per-item results)
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = c5_side(eng, torch, dist, world, rank, dev, stream, peak_info)
+        except Exception as exc:
+            c5 = {"error": repr(exc)}
+        eng.close()
+        torch.cuda.empty_cache()
+        eng = _lib.Engine(local)
+
+    # the inducing-point configurations of BASELINE.json (C3 sparse BGP, C4 MBGP) and the drop-in FitModel calls, N = 1 only:
+    # parity-test cases, reported beside the headline so that their figures come from the same run
     other = None
     if world == 1 and not args.no_sparse:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import time_sparse
-            del keep
-            eng.close()                 # gives back the dense workspace and the optimiser state of the fit (116 GB)
-            torch.cuda.empty_cache()
-            eng = _lib.Engine(local)
-            other = {"note": "bound + gradient evaluations/s with inputs resident in HBM (tools/time_sparse.py); C3: HBM bound, fraction = "
-                             "algorithmic logPhi + gradient bytes (16 B per element) over the measured copy bandwidth; C4: algebra flops "
-                             "D (4 Mz^2 3N + Mz^3) over the measured DMMA peak",
-                     "C3": time_sparse.run("C3 sparse BGP: N=10000, Mz=30", 10000, 1, 30, 8, False, eng=eng, verbose=False),
-                     "C4": time_sparse.run("C4 MBGP: N=500, D=100, Mz=180", 500, 100, 180, 4, True, eng=eng, verbose=False)}
+            other = {"note": "bound + gradient evaluations/s with inputs resident in HBM (tools/time_sparse.py), `e2e` = the same through the "
+                             "host-pointer entry with pinned host buffers (copies inside the timed region); C3: HBM bound, fraction = "
+                             "algorithmic logPhi + gradient bytes (16 B per element) over the measured copy bandwidth, its e2e is bound by "
+                             "PCIe (2.4 GB per item each way); C4: algebra flops D (4 Mz^2 3N + Mz^3) over the measured DMMA peak",
+                     "C3": time_sparse.run("C3 sparse BGP: N=10000, Mz=30", 10000, 1, 30, 8, False, eng=eng, verbose=False, e2e_items=4),
+                     "C4": time_sparse.run("C4 MBGP: N=500, D=100, Mz=180", 500, 100, 180, 4, True, eng=eng, verbose=False, e2e_items=4)}
             # C1 (BASELINE.json configs[0]): the drop-in FitModel call on one synthetic gene, N = 100, 10-point grid -- wall
             # clock of the whole call through the public API, SciPy driver and device-resident batched optimiser
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -395,6 +542,8 @@ def run_ours(args):
                 r1 = fn()
                 c1[name] = {"seconds": round(time.perf_counter() - t0, 3), "argmax_b": round(float(grid1[int(np.argmax(r1["loglik"]))]), 6)}
             other["C1"] = c1
+            other["single_gene_N1000"] = single_gene_fitmodel(eng, H)
+            other["hematopoiesis"] = hematopoiesis_recipe()
         except Exception as exc:   # never lose the headline line to a side measurement
             other = {"error": repr(exc)} if other is None else dict(other, error=repr(exc))
 
@@ -405,7 +554,7 @@ def run_ours(args):
                        "items_per_step_per_gpu": ips, "cells": N, "D": 1, "kernel": "Matern32",
                        "l2": "inputs larger than L2 (logPhi+grad = %.1f GB per step), no flush" % (2 * ips * N * 3 * N * 8 / 1e9),
                        "parallelism": f"items sharded over {world} GPU(s), NCCL all_gather of [items,5] results per step"},
-            "e2e": e2e, "fit": fit, "other_configs": other, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "status_nonzero": bad}
+            "e2e": e2e, "fit": fit, "c5_side": c5, "other_configs": other, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "status_nonzero": bad}
     if rank == 0 and world == 1 and not args.no_cpu:   # reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(N, H, kind="port", budget_s=args.cpu_seconds)
     if rank == 0:
@@ -532,7 +681,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
-    ap.add_argument("--no-sparse", action="store_true", help="skip the C3 / C4 side measurements")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the C3 / C4 / FitModel side measurements")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5-shaped (N = 2000) side line")
     ap.add_argument("--fit-items", type=int, default=148)
     ap.add_argument("--fit-maxiter", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")

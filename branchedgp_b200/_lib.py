@@ -129,6 +129,21 @@ def load_library():
         return lib
 
 
+def pinned_empty(shape):
+    """float64 numpy array in page-locked host memory (bgp_host_alloc): the `_host` entry points then move it at full PCIe speed
+    instead of through the driver's staging copies.  Freed when the last view is garbage collected."""
+    import weakref
+    lib = load_library()
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    n = int(np.prod(shape))
+    p = ctypes.c_void_p()
+    if lib.bgp_host_alloc(ctypes.byref(p), max(n, 1) * 8) != 0 or not p.value:
+        raise BgpError(f"bgp_host_alloc of {n * 8} bytes failed")
+    flat = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), shape=(max(n, 1),))
+    weakref.finalize(flat, lib.bgp_host_free, p)
+    return flat[:n].reshape(shape)
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 

@@ -3,6 +3,11 @@
 
 using namespace bgp;
 
+extern "C" {
+static int ensure_lane_streams(bgp_handle* h, int lanes);
+static int ensure_pin(bgp_handle* h, size_t bytes);
+}
+
 void prof_mark(bgp_handle* h, int phase, cudaStream_t st) {
     if (phase >= 0) h->launches++;
     if (!h->profiling) return;
@@ -335,25 +340,11 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
     const size_t o_lanes = take((size_t)lanes * lo);
     rc = ensure_stage(h, o);
     if (rc != BGP_OK) return rc;
-    while ((int)h->lane_streams.size() < lanes) {
-        // earlier lanes get higher priority so that groups complete roughly in order (their D2H then overlaps later groups)
-        int lo_p = 0, hi_p = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));   // hi_p is numerically the smallest
-        int prio = hi_p + (int)h->lane_streams.size();
-        if (prio > lo_p) prio = lo_p;
-        cudaStream_t s_;
-        CU(cudaStreamCreateWithPriority(&s_, cudaStreamNonBlocking, prio));
-        h->lane_streams.push_back(s_);
-    }
-    if (!h->shared_ready) CU(cudaEventCreateWithFlags(&h->shared_ready, cudaEventDisableTiming));
+    rc = ensure_lane_streams(h, lanes);
+    if (rc != BGP_OK) return rc;
     // small results land in pinned scratch (an async copy into pageable memory would block the host until the group is done)
-    const size_t pin_need = (size_t)count * 48 + (size_t)count * 40;
-    if (h->pin_bytes < pin_need) {
-        if (h->pin) cudaFreeHost(h->pin);
-        h->pin = nullptr; h->pin_bytes = 0;
-        CU(cudaHostAlloc(&h->pin, pin_need, cudaHostAllocDefault));
-        h->pin_bytes = pin_need;
-    }
+    rc = ensure_pin(h, (size_t)count * 48 + (size_t)count * 40);
+    if (rc != BGP_OK) return rc;
     double* pin_elbo = (double*)h->pin;
     double* pin_gh = pin_elbo + count;
     int* pin_st = (int*)(pin_gh + (size_t)4 * count);
@@ -372,7 +363,9 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
     if (KConst) CU(cudaMemcpyAsync(s + o_K, KConst, M * M * 8, cudaMemcpyHostToDevice, s0));
     CU(cudaEventRecord(h->shared_ready, s0));
     for (int l = 1; l < lanes; ++l) CU(cudaStreamWaitEvent(h->lane_streams[l], h->shared_ready, 0));
-    for (int g = 0; g < ngroups && rc == BGP_OK; ++g) {
+    // a failing call inside the loop must not return before the lanes have drained (copies into the caller's arrays may be in flight)
+    auto run = [&]() -> int {
+    for (int g = 0; g < ngroups; ++g) {
         const int l = g % lanes;
         cudaStream_t st = h->lane_streams[l];
         const int i0 = g * gs;
@@ -382,11 +375,11 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
         CU(cudaMemcpyAsync(ls + l_b, pin_b + i0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ls + l_hyp, pin_hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ls + l_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, st));
-        rc = dense_run(h, n, N, D, (double*)(s + o_t), (double*)(s + o_Y), (int*)(ls + l_gene), (double*)(ls + l_b), (double*)(s + o_prior),
+        const int r2 = dense_run(h, n, N, D, (double*)(s + o_t), (double*)(s + o_Y), (int*)(ls + l_gene), (double*)(ls + l_b), (double*)(s + o_prior),
                        (double*)(ls + l_hyp), kernel_kind, model, kl_weight, (double*)(ls + l_lp), KConst ? (double*)(s + o_K) : nullptr,
                        want_grad, (double*)(ls + l_elbo), (double*)(ls + l_gh), want_grad ? (double*)(ls + l_g) : nullptr,
                        (int*)(ls + l_st), (char*)h->ws + (size_t)l * gs * SL.total, gs, st, false, i0, few);
-        if (rc != BGP_OK) break;
+        if (r2 != BGP_OK) return r2;
         CU(cudaMemcpyAsync(pin_elbo + i0, ls + l_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(pin_st + i0, ls + l_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (want_grad) {
@@ -394,6 +387,9 @@ int bgp_dense_elbo_grad_host(bgp_handle* h, int count, int N, int D, const doubl
             CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, ls + l_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
         }
     }
+    return BGP_OK;
+    };
+    rc = run();
     for (int l = 0; l < lanes; ++l) {
         cudaError_t e_ = cudaStreamSynchronize(h->lane_streams[l]);
         if (e_ != cudaSuccess && rc == BGP_OK) rc = fail(h, BGP_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e_));
@@ -487,12 +483,42 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     return BGP_OK;
 }
 
+// Lane streams of the host-pointer entry points; earlier lanes get higher priority so that groups complete roughly in order
+// (their D2H then overlaps later groups).
+static int ensure_lane_streams(bgp_handle* h, int lanes) {
+    while ((int)h->lane_streams.size() < lanes) {
+        int lo_p = 0, hi_p = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));   // hi_p is numerically the smallest
+        int prio = hi_p + (int)h->lane_streams.size();
+        if (prio > lo_p) prio = lo_p;
+        cudaStream_t s_;
+        CU(cudaStreamCreateWithPriority(&s_, cudaStreamNonBlocking, prio));
+        h->lane_streams.push_back(s_);
+    }
+    if (!h->shared_ready) CU(cudaEventCreateWithFlags(&h->shared_ready, cudaEventDisableTiming));
+    return BGP_OK;
+}
+static int ensure_pin(bgp_handle* h, size_t bytes) {
+    if (h->pin_bytes >= bytes) return BGP_OK;
+    if (h->pin) cudaFreeHost(h->pin);
+    h->pin = nullptr; h->pin_bytes = 0;
+    CU(cudaHostAlloc(&h->pin, bytes, cudaHostAllocDefault));
+    h->pin_bytes = bytes;
+    return BGP_OK;
+}
+
+// Host-pointer entry of the inducing-point bounds.  The items are cut into groups that pass through three stages on three
+// streams -- H2D of the group's logPhi, the kernels, D2H of its gradient -- with two staging buffers, so the copies of
+// neighbouring groups run in both PCIe directions at once and hide the (much shorter) arithmetic: at C3 (N = 10 000) an item
+// moves 2.4 GB each way for 3 ms of kernels, i.e. the call is bound by one PCIe direction instead of the sum of both.
 int bgp_sparse_elbo_grad_host(bgp_handle* h, int count, int N, int Dtot, int Mz, const double* t, const double* Z,
                               const double* Y, int nY, const int* item_gene, const double* b, const double* prior,
                               const double* hyp, int kernel_kind, int model, int multi, const double* logPhi, int want_grad,
                               double* elbo, double* grad_hyp, double* grad_b, double* grad_logPhi, int* status) {
     if (!h) return BGP_ERR_ARG;
     if (count <= 0 || N <= 0 || Dtot <= 0 || nY <= 0 || Mz <= 0) return fail(h, BGP_ERR_ARG, "count, N, Dtot, nY, Mz must be positive");
+    if (!t || !Z || !Y || !item_gene || !b || !prior || !hyp || !logPhi || !elbo || !status) return fail(h, BGP_ERR_ARG, "null input pointer");
+    if (want_grad && (!grad_hyp || !grad_logPhi)) return fail(h, BGP_ERR_ARG, "want_grad needs grad_hyp and grad_logPhi");
     CU(cudaSetDevice(h->device));
     const size_t M = 3 * (size_t)N;
     const int pcols = model == BGP_MODEL_MBGP ? 3 : 2;
@@ -502,48 +528,113 @@ int bgp_sparse_elbo_grad_host(bgp_handle* h, int count, int N, int Dtot, int Mz,
     CU(cudaMemGetInfo(&free_b, &total_b));
     const size_t avail = free_b + h->ws_bytes + h->stage_bytes;
     int cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
-    // half of the memory for staging (logPhi + gradient), the rest for the workspace
-    if ((size_t)cap * 2 * per_item > (size_t)(0.45 * (double)avail)) cap = (int)((size_t)(0.45 * (double)avail) / (2 * per_item));
-    if (cap < 1) return fail(h, BGP_ERR_NOMEM, "one sparse work item at N=%d does not fit in device memory", N);
     if (cap > count) cap = count;
+    // half of the memory for staging (two buffers of logPhi + gradient), the rest for the workspace
+    const size_t stage_budget = (size_t)(0.45 * (double)avail);
+    if ((size_t)cap * 2 * per_item > stage_budget) cap = (int)(stage_budget / (2 * per_item));
+    if (cap < 1) return fail(h, BGP_ERR_NOMEM, "one sparse work item at N=%d does not fit in device memory", N);
+    // large transfers: at least four groups so that H2D, kernels and D2H of neighbouring groups overlap
+    if (count > 1 && (size_t)count * per_item > ((size_t)256 << 20)) {
+        const int want = count < 4 ? count : 4;
+        const int c2 = (count + want - 1) / want;
+        if (c2 < cap) cap = c2;
+    }
+    int ngroups = (count + cap - 1) / cap;
+    if (ngroups > 1) {   // several groups: two staging buffers, groups of equal size
+        if ((size_t)cap * 4 * per_item > stage_budget) cap = (int)(stage_budget / (4 * per_item));
+        if (cap < 1) cap = 1;
+        ngroups = (count + cap - 1) / cap;
+        cap = (count + ngroups - 1) / ngroups;
+    }
+    const int nbuf = ngroups > 1 ? 2 : 1;
     const int saved_slots = h->max_slots;
-    h->max_slots = cap;
+    size_t lo = 0;
+    auto ltake = [&](size_t bytes) { size_t r = lo; lo = align_up(lo + bytes, 256); return r; };
+    const size_t l_gene = ltake((size_t)cap * 4), l_b = ltake((size_t)cap * SD * 8), l_hyp = ltake((size_t)cap * 24);
+    const size_t l_elbo = ltake((size_t)cap * 8), l_gh = ltake((size_t)cap * 24), l_gb = ltake((size_t)cap * SD * 8), l_st = ltake((size_t)cap * 4);
+    const size_t l_lp = ltake((size_t)cap * per_item), l_g = ltake(want_grad ? (size_t)cap * per_item : 0);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     const size_t o_t = take((size_t)N * 8), o_Z = take((size_t)Mz * 16), o_Y = take((size_t)nY * N * Dtot * 8);
     const size_t o_prior = take((size_t)N * pcols * 8);
-    const size_t o_gene = take((size_t)cap * 4), o_b = take((size_t)cap * SD * 8), o_hyp = take((size_t)cap * 24);
-    const size_t o_elbo = take((size_t)cap * 8), o_gh = take((size_t)cap * 24), o_gb = take((size_t)cap * SD * 8), o_st = take((size_t)cap * 4);
-    const size_t o_lp = take((size_t)cap * per_item), o_g = take(want_grad ? (size_t)cap * per_item : 0);
+    const size_t o_lanes = take((size_t)nbuf * lo);
     int rc = ensure_stage(h, o);
-    if (rc != BGP_OK) { h->max_slots = saved_slots; return rc; }
+    if (rc != BGP_OK) return rc;
+    rc = ensure_lane_streams(h, 3);
+    if (rc != BGP_OK) return rc;
+    while (h->sp_events.size() < 6) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->sp_events.push_back(e);
+    }
+    // small per-item inputs / results travel through pinned scratch (async copies from / to pageable memory would serialise the lanes)
+    const size_t n_out = (size_t)count * (8 + 24 + (size_t)SD * 8 + 4), n_in = (size_t)count * ((size_t)SD * 8 + 24 + 4);
+    rc = ensure_pin(h, align_up(n_out, 64) + n_in + 64);
+    if (rc != BGP_OK) return rc;
+    double* pin_elbo = (double*)h->pin;
+    double* pin_gh = pin_elbo + count;
+    double* pin_gb = pin_gh + (size_t)3 * count;
+    int* pin_st = (int*)(pin_gb + (size_t)SD * count);
+    double* pin_b = (double*)((char*)h->pin + align_up(n_out, 64));
+    double* pin_hyp = pin_b + (size_t)SD * count;
+    int* pin_gene = (int*)(pin_hyp + (size_t)3 * count);
+    memcpy(pin_b, b, (size_t)count * SD * 8);
+    memcpy(pin_hyp, hyp, (size_t)count * 24);
+    memcpy(pin_gene, item_gene, (size_t)count * 4);
     char* s = (char*)h->stage;
-    cudaStream_t st = 0;
-    CU(cudaMemcpyAsync(s + o_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s + o_Z, Z, (size_t)Mz * 16, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s + o_Y, Y, (size_t)nY * N * Dtot * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s + o_prior, prior, (size_t)N * pcols * 8, cudaMemcpyHostToDevice, st));
-    for (int i0 = 0; i0 < count && rc == BGP_OK; i0 += cap) {
-        const int n = (count - i0 < cap) ? (count - i0) : cap;
-        CU(cudaMemcpyAsync(s + o_gene, item_gene + i0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s + o_b, b + (size_t)i0 * SD, (size_t)n * SD * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s + o_hyp, hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s + o_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, st));
-        rc = bgp_sparse_elbo_grad(h, n, N, Dtot, Mz, (double*)(s + o_t), (double*)(s + o_Z), (double*)(s + o_Y), nY, (int*)(s + o_gene),
-                                  (double*)(s + o_b), (double*)(s + o_prior), (double*)(s + o_hyp), kernel_kind, model, multi,
-                                  (double*)(s + o_lp), want_grad, (double*)(s + o_elbo), (double*)(s + o_gh), (double*)(s + o_gb),
-                                  want_grad ? (double*)(s + o_g) : nullptr, (int*)(s + o_st), st);
-        if (rc != BGP_OK) break;
-        CU(cudaMemcpyAsync(elbo + i0, s + o_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(status + i0, s + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (want_grad) {
-            CU(cudaMemcpyAsync(grad_hyp + (size_t)i0 * 3, s + o_gh, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
-            if (grad_b) CU(cudaMemcpyAsync(grad_b + (size_t)i0 * SD, s + o_gb, (size_t)n * SD * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, s + o_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, st));
+    cudaStream_t s_in = h->lane_streams[0], s_cmp = h->lane_streams[1], s_out = h->lane_streams[2];
+    CU(cudaMemcpyAsync(s + o_t, t, (size_t)N * 8, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(s + o_Z, Z, (size_t)Mz * 16, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(s + o_Y, Y, (size_t)nY * N * Dtot * 8, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(s + o_prior, prior, (size_t)N * pcols * 8, cudaMemcpyHostToDevice, s_in));
+    h->max_slots = cap;
+    auto run = [&]() -> int {
+        for (int g = 0; g < ngroups; ++g) {
+            const int buf = g % nbuf;
+            cudaEvent_t in_ev = h->sp_events[buf], done_ev = h->sp_events[2 + buf], free_ev = h->sp_events[4 + buf];
+            const int i0 = g * cap;
+            const int n = (count - i0 < cap) ? (count - i0) : cap;
+            char* ls = s + o_lanes + (size_t)buf * lo;
+            if (g >= nbuf) CU(cudaStreamWaitEvent(s_in, free_ev, 0));   // the buffer's previous gradient is home
+            CU(cudaMemcpyAsync(ls + l_gene, pin_gene + i0, (size_t)n * 4, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync(ls + l_b, pin_b + (size_t)i0 * SD, (size_t)n * SD * 8, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync(ls + l_hyp, pin_hyp + (size_t)i0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync(ls + l_lp, logPhi + (size_t)i0 * N * M, (size_t)n * per_item, cudaMemcpyHostToDevice, s_in));
+            CU(cudaEventRecord(in_ev, s_in));
+            CU(cudaStreamWaitEvent(s_cmp, in_ev, 0));
+            int r2 = bgp_sparse_elbo_grad(h, n, N, Dtot, Mz, (double*)(s + o_t), (double*)(s + o_Z), (double*)(s + o_Y), nY, (int*)(ls + l_gene),
+                                          (double*)(ls + l_b), (double*)(s + o_prior), (double*)(ls + l_hyp), kernel_kind, model, multi,
+                                          (double*)(ls + l_lp), want_grad, (double*)(ls + l_elbo), (double*)(ls + l_gh), (double*)(ls + l_gb),
+                                          want_grad ? (double*)(ls + l_g) : nullptr, (int*)(ls + l_st), s_cmp);
+            if (r2 != BGP_OK) return r2;
+            CU(cudaEventRecord(done_ev, s_cmp));
+            CU(cudaStreamWaitEvent(s_out, done_ev, 0));
+            CU(cudaMemcpyAsync(pin_elbo + i0, ls + l_elbo, (size_t)n * 8, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync(pin_st + i0, ls + l_st, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
+            if (want_grad) {
+                CU(cudaMemcpyAsync(pin_gh + (size_t)i0 * 3, ls + l_gh, (size_t)n * 24, cudaMemcpyDeviceToHost, s_out));
+                CU(cudaMemcpyAsync(pin_gb + (size_t)i0 * SD, ls + l_gb, (size_t)n * SD * 8, cudaMemcpyDeviceToHost, s_out));
+                CU(cudaMemcpyAsync(grad_logPhi + (size_t)i0 * N * M, ls + l_g, (size_t)n * per_item, cudaMemcpyDeviceToHost, s_out));
+            }
+            CU(cudaEventRecord(free_ev, s_out));
         }
-        CU(cudaStreamSynchronize(st));
+        return BGP_OK;
+    };
+    rc = run();
+    // common epilogue, also after an error: nothing may still be writing into the caller's arrays when this function returns
+    for (cudaStream_t st : {s_in, s_cmp, s_out}) {
+        cudaError_t e_ = cudaStreamSynchronize(st);
+        if (e_ != cudaSuccess && rc == BGP_OK) rc = fail(h, BGP_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e_));
     }
     h->max_slots = saved_slots;
+    if (rc == BGP_OK) {
+        memcpy(elbo, pin_elbo, (size_t)count * 8);
+        memcpy(status, pin_st, (size_t)count * 4);
+        if (want_grad) {
+            memcpy(grad_hyp, pin_gh, (size_t)count * 24);
+            if (grad_b) memcpy(grad_b, pin_gb, (size_t)count * SD * 8);
+        }
+    }
     return rc;
 }
 

@@ -120,41 +120,88 @@ __device__ __forceinline__ void tile_mm_strip(double* C, int ldc, double c0, dou
 }
 
 // In-place lower Cholesky of Dm (row-major, leading dimension DLD).  Non-positive pivots are replaced by 1 and reported.
-// Right-looking over 32-column panels.
+// Right-looking over 8-column blocks (16 steps of three CTA barriers).  A measurement of the multi-CTA pipeline
+// (tools/wide_timers.py) put the previous version -- 32-column panels, the 32x32 diagonal tile factored AND inverted by one warp
+// through shared memory -- at 90 us per block, 60 % of the critical path of the tile Cholesky.  Here the serial part of a step
+// is an 8x8 diagonal block in the registers of one warp (pivots and multipliers travel by shuffles, one rsqrt per pivot, no
+// inverse: the panel rows are forward-substituted, one thread per row) and the rank-8 trailing update runs as 8x8 DMMA tiles
+// over all sixteen warps.
 static __device__ void chol128(double* Dm, int& fail, int base_index) {
     __shared__ int fail_s;
+    __shared__ double rinv_s[8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, grp = warp >> 2;   // 8-row strip and tile-product slot of this warp
-    double* Winv = Dm + MB * DLD;               // inverse of the current diagonal tile
-    __syncthreads();
-    for (int p = 0; p < TPM; ++p) {
-        double* Tpp = Dm + (TS * p) * DLD + TS * p;
+    const int g = lane >> 2, c = lane & 3;
+    constexpr int NB8 = MB / 8;
+    if (tid == 0) fail_s = 0;
+    for (int J = 0; J < NB8; ++J) {
+        const int j0 = 8 * J;
+        __syncthreads();
         if (warp == 0) {
-            chol32_warp(Tpp, DLD, fail, base_index + TS * p, lane);
-            trinv32_warp(Tpp, DLD, Winv, TLD, lane);
+            // 8x8 diagonal block, lane = row (lanes 8..31 carry identity rows)
+            double a[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = (lane < 8 && k <= lane) ? Dm[(j0 + lane) * DLD + j0 + k] : ((k == lane) ? 1.0 : 0.0);
+            double rinv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double sacc = a[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) sacc = fma(-a[k], __shfl_sync(0xffffffffu, a[k], j), sacc);
+                double d = __shfl_sync(0xffffffffu, sacc, j);
+                if (!(d > 0.0)) {
+                    if (lane == 0 && fail_s == 0) fail_s = base_index + j0 + j + 1;
+                    d = 1.0;
+                }
+                rinv[j] = rsqrt(d);
+                a[j] = (lane < j) ? 0.0 : ((lane == j) ? d * rinv[j] : sacc * rinv[j]);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k <= lane) Dm[(j0 + lane) * DLD + j0 + k] = a[k];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rinv_s[k] = rinv[k];
+            }
         }
         __syncthreads();
-        // panel: L_ip = A_ip inv(L_pp)^T
-        if (grp < TPM - 1 - p) {
-            double* Aip = Dm + (TS * (p + 1 + grp)) * DLD + TS * p;
-            tile_mm_strip<true>(Aip, DLD, 0.0, 1.0, Aip, DLD, Winv, TLD, 8 * q, lane);
-        }
-        __syncthreads();
-        // trailing tiles (i, jt), p < jt <= i: A_ij -= L_ip L_jp^T  (at most six, four at a time)
+        // panel row i:  L_i L_JJ^T = A_i  by forward substitution
         {
-            int idx = 0;
-            for (int i = p + 1; i < TPM; ++i)
-                for (int jt = p + 1; jt <= i; ++jt, ++idx)
-                    if ((idx & 3) == grp)
-                        tile_mm_strip<true>(Dm + (TS * i) * DLD + TS * jt, DLD, 1.0, -1.0, Dm + (TS * i) * DLD + TS * p, DLD,
-                                            Dm + (TS * jt) * DLD + TS * p, DLD, 8 * q, lane);
+            const int i = j0 + 8 + tid;
+            if (i < MB) {
+                double* row = Dm + i * DLD + j0;
+                const double* Ld = Dm + j0 * DLD + j0;
+                double l[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    double sacc = row[cc];
+#pragma unroll
+                    for (int k = 0; k < cc; ++k) sacc = fma(-l[k], Ld[cc * DLD + k], sacc);
+                    l[cc] = sacc * rinv_s[cc];
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) row[cc] = l[cc];
+            }
         }
         __syncthreads();
+        // trailing 8x8 tiles (rt, ct), J < ct <= rt: D -= L_rt L_ct^T (two DMMAs each), dealt to the warps
+        const int T0 = J + 1, nrem = NB8 - T0;
+        int rr = 0, cr = warp;
+        for (int t8 = warp; t8 < nrem * (nrem + 1) / 2; t8 += GEMM_WARPS, cr += GEMM_WARPS) {
+            while (cr > rr) { cr -= rr + 1; ++rr; }
+            double* dp = Dm + (8 * (T0 + rr) + g) * DLD + 8 * (T0 + cr) + 2 * c;
+            double d0 = dp[0], d1 = dp[1];
+            const double* ar = Dm + (8 * (T0 + rr) + g) * DLD + j0 + c;
+            const double* br = Dm + (8 * (T0 + cr) + g) * DLD + j0 + c;
+            dmma(d0, d1, -ar[0], br[0]);
+            dmma(d0, d1, -ar[4], br[4]);
+            dp[0] = d0;
+            dp[1] = d1;
+        }
     }
-    // the pivot checks ran in warp 0 only: share its verdict
-    if (tid == 0) fail_s = fail;
     __syncthreads();
-    fail = fail_s;
+    if (fail == 0) fail = fail_s;
     __syncthreads();
 }
 

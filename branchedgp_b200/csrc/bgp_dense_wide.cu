@@ -707,12 +707,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
     auto Pscr = [&](int I) { return PB + (size_t)(I - 1) * 16 * TILE_ELEMS; };
     auto Qscr = [&](int I) { return PB + (size_t)(nM - 1 + I - 1) * 16 * TILE_ELEMS; };
     int ntasks = 1;
-    for (int K = nM - 1; K >= 1; --K) ntasks += (nM - K) + 1 + (K >= 2 ? (K - 1) * (nM - K) : 0);
+    for (int K = nM - 1; K >= 1; --K) ntasks += (nM - K) + 1 + (K >= 2 ? 1 + (K - 1) * (nM - K) : 0);
+    int* hpcnt = C.head + 1;   // hyper-gradient partials written so far
+    int* qsflag = C.fail;      // qsflag[J]: the Q partials of column J have been summed into the Q block of row J
     Acc acc;
     for (;;) {
         const int t = wq_next(C.head, &s_task);
         if (t >= ntasks) break;
-        int type = 0, I = 0, J = 0, K = 0;   // 0 ADIAG(J), 1 APANEL(I,J), 2 BROW(I=K,J), 3 SC(I,J;K)
+        int type = 0, I = 0, J = 0, K = 0;   // 0 ADIAG(J), 1 APANEL(I,J), 2 BROW(I=K,J), 3 SC(I,J;K), 4 QSUM(J)
         if (t == 0) { type = 0; J = nM - 1; }
         else {
             int u = t - 1;
@@ -722,6 +724,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                 u -= na;
                 if (u == 0) { type = 0; J = K - 1; break; }
                 u -= 1;
+                if (K >= 2) {
+                    if (u == 0) { type = 4; J = K - 1; break; }
+                    u -= 1;
+                }
                 const int nb = K >= 2 ? K - 1 : 0;
                 if (u < nb) { type = 2; I = K; J = K - 2 - u; break; }
                 u -= nb;
@@ -733,27 +739,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
         double gl = 0.0, gv = 0.0, gb = 0.0;
         if (type == 1) {
             // ---- panel tile (I, J) of column J = K - 1
+            WT_DECL();
+            WT_COUNT(I == K ? 16 : 24);
             const double* blk = LinvD + (size_t)J * 16 * TILE_ELEMS;
             const Opnd opInvCol = opnd_block(blk, ACC_COLK, TPM * J, TPM * J, 1);
             if (I == K) {
                 // E = Lbar[K,J] - Atilde_KK Lc[K,J] - sum_{k>K} Q_k   (Q_k = Atilde[k,K]^T Lc[k,J], left by the panel tasks of column K)
                 if (tid == 0) {
                     spin_ge(&C.fin[tix(K, K)], 1);
-                    for (int k = K + 1; k < nM; ++k) spin_ge(&C.fin[tix(k, K)], 1);
+                    if (K + 1 < nM) spin_ge(&qsflag[K], 1);
                 }
                 deps_ready();
+                WT_LAP(17);
                 acc_zero(acc);
                 gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * K, min(TPM * K + TPM, nT), nullptr);
                 acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                     double* tp = LB + packed_tile(it, jt) * TILE_ELEMS;
                     const double2 l = tile_load2_cg(tp, i, j);
                     const size_t qo = (size_t)((it - TPM * I) * TPM + (jt - TPM * J)) * TILE_ELEMS;
-                    double q0 = 0.0, q1 = 0.0;
-                    for (int k = K + 1; k < nM; ++k) {
-                        const double2 qk = tile_load2_cg(Qscr(k) + qo, i, j);
-                        q0 += qk.x; q1 += qk.y;
-                    }
-                    tile_store2(tp, i, j, l.x - v0 - q0, l.y - v1 - q1);
+                    double2 q = make_double2(0.0, 0.0);
+                    if (K + 1 < nM) q = tile_load2_cg(Qscr(K) + qo, i, j);   // sum_{k>K} Q_k, summed in row order by QSUM(K)
+                    tile_store2(tp, i, j, l.x - v0 - q.x, l.y - v1 - q.y);
                 });
             } else {
                 // E = (Lbar[I,J] with the scatters of columns > K already applied) - Atilde[I,K] Lc[K,J]
@@ -762,6 +768,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                     if (I - J - 1 > 0) spin_ge(&C.cnt[tix(I, J)], I - J - 1);
                 }
                 deps_ready();
+                WT_LAP(25);
                 acc_zero(acc);
                 gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * K, min(TPM * K + TPM, nT), nullptr);
                 acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
@@ -771,18 +778,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                 });
             }
             fence_proxy_async();
+            WT_LAP(I == K ? 18 : 26);
             // Atilde[I,J] = E inv(L_JJ)
             acc_zero(acc);
             gemm_macro(acc, pipe, opArow, TPM * I, opInvCol, TPM * J, TPM * J, TPM * J + TPM, nullptr, 0);   // the skipped operand is B
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 tile_store2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j, v0, v1);
-                if (want_hyp) {
-                    const int gi = it * TS + i, gj = jt * TS + j;
-                    hyper_accum(P, ka, dkal, dkab, KT, gi, gj, v0, kvar, kinv, gl, gv, gb);
-                    hyper_accum(P, ka, dkal, dkab, KT, gi, gj + 1, v1, kvar, kinv, gl, gv, gb);
-                }
             }, 0);
             fence_proxy_async();
+            WT_LAP(I == K ? 19 : 27);
             // P_I = Atilde[I,J]^T Lc[I,J]  (lower warp tiles) for the diagonal task of column J
             acc_zero(acc);
             gemm_macro(acc, pipe, opAcol, TPM * J, opLcol, TPM * J, TPM * I, min(TPM * I + TPM, nT), nullptr, 2);
@@ -797,6 +801,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                 tile_store2(Pscr(I) + (size_t)((it - TPM * J) * TPM + (jt - TPM * J)) * TILE_ELEMS, i, j, v0, v1);
             }, 2);
             task_signal_add(&C.col[J]);
+            WT_LAP(I == K ? 20 : 28);
             // Q_I = Atilde[I,J]^T Lc[I,J-1]  for the panel tile (J, J-1) of the next column
             if (J >= 1) {
                 acc_zero(acc);
@@ -809,33 +814,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                     tile_store2(Qscr(I) + (size_t)((it - TPM * J) * TPM + (jt - TPM * (J - 1))) * TILE_ELEMS, i, j, v0, v1);
                 });
             }
-            if (want_hyp) {
-                gl = block_sum(gl, red); gv = block_sum(gv, red); gb = block_sum(gb, red);
-                if (tid == 0) { double* h3 = hp + (size_t)tix(I, J) * 3; h3[0] = gl; h3[1] = gv; h3[2] = gb; }
-            }
             task_signal(&C.fin[tix(I, J)], 1);
+            // off the dependency chain: this tile's share of sum(Atilde o dK/dtheta), read back from the finished tile
+            if (want_hyp) {
+                acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double, double) {
+                    const double2 w = tile_load2(LB + packed_tile(it, jt) * TILE_ELEMS, i, j);
+                    const int gi = it * TS + i, gj = jt * TS + j;
+                    hyper_accum(P, ka, dkal, dkab, KT, gi, gj, w.x, kvar, kinv, gl, gv, gb);
+                    hyper_accum(P, ka, dkal, dkab, KT, gi, gj + 1, w.y, kvar, kinv, gl, gv, gb);
+                });
+                gl = block_sum(gl, red); gv = block_sum(gv, red); gb = block_sum(gb, red);
+                if (tid == 0) {
+                    double* h3 = hp + (size_t)tix(I, J) * 3;
+                    h3[0] = gl; h3[1] = gv; h3[2] = gb;
+                    __threadfence();
+                    atomicAdd(hpcnt, 1);
+                }
+            }
+            WT_LAP(I == K ? 21 : 29);
         } else if (type == 0) {
             // ---- diagonal block J:  Leff = tril(Lbar_JJ) - tril(sum_{I>J} P_I);  Atilde_JJ = sym(inv(L)^T Phi(L^T Leff) inv(L))
             const double* blk = LinvD + (size_t)J * 16 * TILE_ELEMS;
             const Opnd opInvCol = opnd_block(blk, ACC_COLK, TPM * J, TPM * J, 1);
+            WT_DECL();
+            WT_COUNT(32);
             if (tid == 0) spin_ge(&C.col[J], nM - 1 - J);
             deps_ready();
-            for (int a = 0; a < TPM; ++a)
-                for (int b = 0; b < TPM; ++b) {
-                    double* so = S0 + (size_t)(a * TPM + b) * TILE_ELEMS;
-                    const double* lt = LB + packed_tile(TPM * J + a, TPM * J + (b <= a ? b : a)) * TILE_ELEMS;
-                    for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
-                        const int i = e >> 5, j = e & 31;
-                        double val = 0.0;
-                        if (b < a || (b == a && j <= i)) {
-                            val = lt[tswz(i, j)];
-                            const size_t po = (size_t)(a * TPM + b) * TILE_ELEMS + tswz(i, j);
-                            for (int I2 = J + 1; I2 < nM; ++I2) val -= __ldcg(Pscr(I2) + po);
-                        }
-                        so[tswz(i, j)] = val;
-                    }
+            WT_LAP(33);
+            {
+                // 10 lower tiles x 1024 elements = 20 per thread, kept in registers while the partial blocks stream by: the loads of
+                // one partial are independent of each other (the element-by-element version spent 24 us here, latency bound)
+                constexpr int PER = 10 * TILE_ELEMS / GEMM_THREADS;
+                double val[PER];
+                int off[PER];
+                unsigned live = 0;
+#pragma unroll
+                for (int r = 0; r < PER; ++r) {
+                    const int e = tid + GEMM_THREADS * r, tl = e >> 10, o = e & (TILE_ELEMS - 1);
+                    int a = 0;
+                    while ((a + 1) * (a + 2) / 2 <= tl) ++a;
+                    const int b = tl - a * (a + 1) / 2;
+                    const int i = o >> 5, j = (o & 31) ^ ((i & 3) << 2);   // storage position o holds element (i, j)
+                    off[r] = (a * TPM + b) * TILE_ELEMS + o;
+                    const bool use = b < a || j <= i;
+                    live |= (use ? 1u : 0u) << r;
+                    val[r] = use ? LB[packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS + o] : 0.0;
                 }
+                for (int I2 = J + 1; I2 < nM; ++I2) {
+                    const double* pp = Pscr(I2);
+                    double pv[PER];
+#pragma unroll
+                    for (int r = 0; r < PER; ++r) pv[r] = __ldcg(pp + off[r]);
+#pragma unroll
+                    for (int r = 0; r < PER; ++r) val[r] -= pv[r];
+                }
+#pragma unroll
+                for (int r = 0; r < PER; ++r) S0[off[r]] = ((live >> r) & 1u) ? val[r] : 0.0;
+                // the six tiles above the diagonal are structural zeros of Leff
+                for (int e = tid; e < 6 * TILE_ELEMS; e += GEMM_THREADS) {
+                    const int t6 = e >> 10, o = e & (TILE_ELEMS - 1);
+                    const int a = t6 < 3 ? 0 : (t6 < 5 ? 1 : 2);
+                    const int b = t6 < 3 ? t6 + 1 : (t6 < 5 ? t6 - 1 : 3);
+                    S0[(size_t)(a * TPM + b) * TILE_ELEMS + o] = 0.0;
+                }
+            }
             fence_proxy_async();
+            WT_LAP(34);
             // U = Phi(L_JJ^T Leff)
             acc_zero(acc);
             gemm_macro(acc, pipe, opLcol, TPM * J, opnd_block(S0, ACC_COLK, TPM * J, TPM * J, 0), TPM * J, TPM * J, TPM * J + TPM, nullptr);
@@ -863,6 +907,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                 tile_store2(S1 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, v0, v1);
             }, 0);
             __syncthreads();
+            WT_LAP(35);
             // Atilde_JJ = S + S^T  (diagonal tiles stored fully symmetric)
             for (int a = 0; a < TPM; ++a)
                 for (int b = 0; b <= a; ++b) {
@@ -873,20 +918,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                         const int i = e >> 5, j = e & 31;
                         const double w = sab[tswz(i, j)] + sba[tswz(j, i)];
                         tp[tswz(i, j)] = w;
-                        if (want_hyp) hyper_accum(P, ka, dkal, dkab, KT, (TPM * J + a) * TS + i, (TPM * J + b) * TS + j, w, kvar, kinv, gl, gv, gb);
                     }
                 }
+            task_signal(&C.fin[tix(J, J)], 1);
+            WT_LAP(36);
             if (want_hyp) {
+                // off the dependency chain: the diagonal block's share of sum(Atilde o dK/dtheta)
+                for (int a = 0; a < TPM; ++a)
+                    for (int b = 0; b <= a; ++b) {
+                        const double* tp = LB + packed_tile(TPM * J + a, TPM * J + b) * TILE_ELEMS;
+                        for (int e = tid; e < TILE_ELEMS; e += GEMM_THREADS) {
+                            const int i = e >> 5, j = e & 31;
+                            hyper_accum(P, ka, dkal, dkab, KT, (TPM * J + a) * TS + i, (TPM * J + b) * TS + j, tp[tswz(i, j)], kvar, kinv, gl, gv, gb);
+                        }
+                    }
                 gl = block_sum(gl, red); gv = block_sum(gv, red); gb = block_sum(gb, red);
                 if (tid == 0) { double* h3 = hp + (size_t)tix(J, J) * 3; h3[0] = gl; h3[1] = gv; h3[2] = gb; }
                 if (J == 0) {
-                    // last task of the phase: the panel tasks of column 0 have signalled their P partial but may still be writing
-                    // their hyper-gradient partial (it precedes `fin`); everything else precedes them transitively.  Then sum
-                    // the per-tile partials in a fixed order.
-                    if (tid == 0)
-                        for (int I2 = 1; I2 < nM; ++I2) spin_ge(&C.fin[tix(I2, 0)], 1);
-                    __syncthreads();
+                    // last task of the phase: wait until every other tile has published its partial, then sum them in a fixed order
                     const int nt = nM * (nM + 1) / 2;
+                    if (tid == 0) spin_ge(hpcnt, nt - 1);
+                    __syncthreads();
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
                     for (int e = tid; e < nt; e += GEMM_THREADS) {
                         a0 += __ldcg(hp + (size_t)e * 3 + 0);
@@ -899,20 +951,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                         P.grad_hyp[(size_t)item * 4 + 1] = a1;
                         P.grad_hyp[(size_t)item * 4 + 3] = a2;
                     }
+                } else if (tid == 0) {
+                    __threadfence();
+                    atomicAdd(hpcnt, 1);
                 }
             } else if (J == 0 && tid == 0) {
                 P.grad_hyp[(size_t)item * 4 + 0] = 0.0;
                 P.grad_hyp[(size_t)item * 4 + 1] = 0.0;
                 P.grad_hyp[(size_t)item * 4 + 3] = 0.0;
             }
-            task_signal(&C.fin[tix(J, J)], 1);
+        } else if (type == 4) {
+            // ---- QSUM(J): Q block of row J <- sum_{k>J} Q_k (row order), beside the diagonal task of column J instead of inside the
+            // panel task (J, J-1) that needs it
+            if (tid == 0)
+                for (int k = J + 1; k < nM; ++k) spin_ge(&C.fin[tix(k, J)], 1);
+            __syncthreads();
+            constexpr int PERQ = 16 * TILE_ELEMS / (2 * GEMM_THREADS);   // double2 per thread
+            double2 q[PERQ];
+#pragma unroll
+            for (int r = 0; r < PERQ; ++r) q[r] = make_double2(0.0, 0.0);
+            for (int k = J + 1; k < nM; ++k) {
+                const double2* src = reinterpret_cast<const double2*>(Qscr(k));
+                double2 v[PERQ];
+#pragma unroll
+                for (int r = 0; r < PERQ; ++r) v[r] = __ldcg(src + tid + GEMM_THREADS * r);
+#pragma unroll
+                for (int r = 0; r < PERQ; ++r) { q[r].x += v[r].x; q[r].y += v[r].y; }
+            }
+            double2* dstq = reinterpret_cast<double2*>(Qscr(J));
+#pragma unroll
+            for (int r = 0; r < PERQ; ++r) dstq[tid + GEMM_THREADS * r] = q[r];
+            task_signal(&qsflag[J], 1);
         } else if (type == 2) {
+            WT_DECL();
+            WT_COUNT(38);
             // ---- BROW(K, J): tile (K,J) -= Atilde_sym[K, K:] Lc[K:, J]   (one long product over the rows >= K of column K)
             if (tid == 0) {
                 spin_ge(&C.fin[tix(I, I)], 1);
                 for (int k = I + 1; k < nM; ++k) spin_ge(&C.fin[tix(k, I)], 1);
             }
             deps_ready();
+            WT_LAP(39);
             acc_zero(acc);
             gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * I, nT, nullptr);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
@@ -921,13 +1000,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                 tile_store2(tp, i, j, l.x - v0, l.y - v1);
             });
             task_signal(&C.cnt[tix(I, J)], 1);
+            WT_LAP(40);
         } else {
+            WT_DECL();
+            WT_COUNT(42);
             // ---- SC(I, J; K): tile (I,J) -= Atilde[I,K] Lc[K,J],  I > K > J + 1
             if (tid == 0) {
                 spin_ge(&C.fin[tix(I, K)], 1);
                 spin_ge(&C.cnt[tix(I, J)], I - K);
             }
             deps_ready();
+            WT_LAP(43);
             acc_zero(acc);
             gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * K, min(TPM * K + TPM, nT), nullptr);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
@@ -936,6 +1019,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                 tile_store2(tp, i, j, l.x - v0, l.y - v1);
             });
             task_signal(&C.cnt[tix(I, J)], I - K + 1);
+            WT_LAP(44);
         }
     }
 }

@@ -457,11 +457,14 @@ static int fit_core(FitShared& F, Evaluator& ev, int S, FitVecs V, cudaStream_t 
     // small device / pinned buffers
     double *d_part1 = nullptr, *d_partG = nullptr, *d_coef = nullptr, *d_stp = nullptr;
     int *d_act = nullptr, *d_pos = nullptr, *d_valid = nullptr, *d_newpos = nullptr;
-    CU(cudaMalloc(&d_part1, (size_t)S * FIT_PARTS * 3 * 8));
-    CU(cudaMalloc(&d_partG, (size_t)S * FIT_PARTS * 3 * W * 8));
-    CU(cudaMalloc(&d_coef, (size_t)S * W * 8));
-    CU(cudaMalloc(&d_stp, (size_t)S * 8));
-    CU(cudaMalloc(&d_act, (size_t)S * 4 * 4));
+    // freed on every way out of this function, including the early returns of CU() inside the round loop
+    struct DevGuard { std::vector<void*> p; ~DevGuard() { for (void* q : p) cudaFree(q); } } guard;
+    auto dmalloc = [&](void** q, size_t bytes) -> cudaError_t { cudaError_t e = cudaMalloc(q, bytes); if (e == cudaSuccess) guard.p.push_back(*q); return e; };
+    CU(dmalloc((void**)&d_part1, (size_t)S * FIT_PARTS * 3 * 8));
+    CU(dmalloc((void**)&d_partG, (size_t)S * FIT_PARTS * 3 * W * 8));
+    CU(dmalloc((void**)&d_coef, (size_t)S * W * 8));
+    CU(dmalloc((void**)&d_stp, (size_t)S * 8));
+    CU(dmalloc((void**)&d_act, (size_t)S * 4 * 4));
     d_pos = d_act + S; d_valid = d_pos + S; d_newpos = d_valid + S;
     std::vector<double> part1((size_t)S * FIT_PARTS * 3), partG((size_t)S * FIT_PARTS * 3 * W), coef((size_t)S * W), stpv(S);
     std::vector<double> hyp_c((size_t)S * 3), bv((size_t)S * b_per_item), elbo(S), gh((size_t)S * F.gh_stride);
@@ -471,7 +474,7 @@ static int fit_core(FitShared& F, Evaluator& ev, int S, FitVecs V, cudaStream_t 
     for (auto& s : slots) { s.H.m = m; s.ls = LineSearch(); }
     int next_item = 0, done = 0;
     const dim3 grid(FIT_PARTS, S);
-    auto cleanup = [&]() { cudaFree(d_part1); cudaFree(d_partG); cudaFree(d_coef); cudaFree(d_stp); cudaFree(d_act); };
+    auto cleanup = [&]() {};   // the guard above owns the buffers
 
     auto constrained = [&](const Slot& s, double* out) { for (int k = 0; k < 3; ++k) out[k] = softplus(s.u[k]) + HYP_LOWER[k]; };
     auto log_prior = [&](const double* hc) {

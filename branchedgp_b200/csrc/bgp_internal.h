@@ -34,6 +34,7 @@ struct bgp_handle {
     bool kernels_ready = false;
     std::vector<cudaStream_t> lane_streams;   // streams of the host-pointer entry points (one per in-flight item group)
     cudaEvent_t shared_ready = nullptr;
+    std::vector<cudaEvent_t> sp_events;       // stage hand-off events of the pipelined sparse host entry
     void* pin = nullptr;       // pinned host scratch for the small per-item results of the host-pointer entry points
     size_t pin_bytes = 0;
     // optional per-kernel timing (bench.py): events recorded around every launch of a call

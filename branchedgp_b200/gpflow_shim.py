@@ -104,15 +104,38 @@ class Parameter:
         self.trainable = bool(trainable)
         self.name = name
         self._u = None
+        self._pinned = False
         self.assign(value)
 
     # constrained view
     def numpy(self):
         return np.array(self.transform.forward(self._u), dtype=np.float64)
 
+    def view(self):
+        """Constrained value WITHOUT a copy when there is no transform (the N x 3N assignment logits: 24 MB at N = 1000 that
+        would otherwise be copied on every function evaluation); read-only use."""
+        if isinstance(self.transform, Identity):
+            return self._u
+        return self.numpy()
+
     def assign(self, value):
         v = np.array(value, dtype=np.float64)
-        self._u = np.array(self.transform.inverse(v), dtype=np.float64)
+        u = np.asarray(self.transform.inverse(v), dtype=np.float64)
+        if self._pinned and self._u is not None and u.shape == self._u.shape:
+            np.copyto(self._u, u)          # keep the page-locked storage
+        else:
+            self._u = np.array(u, dtype=np.float64)
+            self._pinned = False
+        return self
+
+    def pin(self, alloc):
+        """Move the storage into page-locked host memory (``alloc(shape)`` -> float64 array, e.g. ``_lib.pinned_empty``) so
+        that the host-pointer CUDA entry points read it by DMA.  No-op when already pinned."""
+        if not self._pinned:
+            buf = alloc(self._u.shape)
+            np.copyto(buf, self._u)
+            self._u = buf
+            self._pinned = True
         return self
 
     @property
@@ -120,7 +143,11 @@ class Parameter:
         return self._u
 
     def set_unconstrained(self, u):
-        self._u = np.array(u, dtype=np.float64).reshape(self._u.shape)
+        u = np.asarray(u, dtype=np.float64).reshape(self._u.shape)
+        if self._pinned:
+            np.copyto(self._u, u)
+        else:
+            self._u = np.array(u, dtype=np.float64)
 
     @property
     def shape(self):
@@ -284,10 +311,29 @@ class Scipy:
                 p.set_unconstrained(x[o:o + n])
                 o += n
 
+        # the packed gradient is written in place, variable by variable (for the N x 3N logits that is one pass over 24 MB at
+        # N = 1000 instead of a negation, a product with the transform's derivative and a concatenation); two buffers are used
+        # in turn because SciPy may still hold the array returned by the previous evaluation
+        gpack = [np.empty(sum(sizes)), np.empty(sum(sizes))]
+        turn = [0]
+        import inspect
+        in_place = "out" in inspect.signature(model._loss_and_grad).parameters
+
         def fun(x):
             unpack(x)
-            loss, grads = model._loss_and_grad(variables)
-            return loss, np.concatenate([g.ravel() for g in grads])
+            buf = gpack[turn[0]]
+            turn[0] ^= 1
+            outs, o = [], 0
+            for p, n in zip(variables, sizes):
+                outs.append(buf[o:o + n].reshape(p.shape))
+                o += n
+            if in_place:
+                loss, _ = model._loss_and_grad(variables, out=outs)
+            else:                      # a model without the in-place variant
+                loss, grads = model._loss_and_grad(variables)
+                for dst, g in zip(outs, grads):
+                    np.copyto(dst, np.asarray(g).reshape(dst.shape))
+            return loss, buf
 
         cb = None
         if step_callback is not None:

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from branchedgp_b200 import _lib  # noqa: E402
 
 
-def run(name, N, Dtot, Mz, count, multi, reps=3, eng=None, verbose=True):
+def run(name, N, Dtot, Mz, count, multi, reps=3, eng=None, verbose=True, e2e_items=0):
     """Times `count` work items of one inducing-point configuration with device-resident inputs; returns the result line as a dict
     (phases_ms = CUDA-event time per pipeline phase of one call)."""
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -90,6 +90,27 @@ def run(name, N, Dtot, Mz, count, multi, reps=3, eng=None, verbose=True):
            "frac_hbm_peak_algorithmic": round(gbps / hbm_peak, 4), "algebra_TFLOPs": round(tflops, 3),
            "frac_dmma_peak": round(tflops / dmma_peak, 4),
            "status_nonzero": int((st != 0).sum().item()), "elbo0": float(elbo[0].item())}
+    if e2e_items > 0:
+        # end to end: the same evaluations through the host-pointer entry (bgp_sparse_elbo_grad_host), logits and gradient in
+        # pinned host memory, host<->device copies inside the timed region
+        import time
+        ne = min(e2e_items, count)
+        h_lp = _lib.pinned_empty((ne, N, M))
+        h_lp[:] = logPhi[:ne].cpu().numpy()
+        h_g = _lib.pinned_empty((ne, N, M))
+        hb = b[:ne].cpu().numpy()
+        hargs = (t.cpu().numpy(), Z.cpu().numpy(), Y.cpu().numpy(), np.zeros(ne, dtype=np.int32), hb if multi else hb[:, 0],
+                 prior.cpu().numpy(), hyp[:ne].cpu().numpy(), h_lp)
+        kw = dict(kernel=1 if multi else 0, model=1 if multi else 0, multi=multi, grad_out=h_g)
+        del gl
+        torch.cuda.empty_cache()
+        eng.sparse_elbo_grad(*hargs, **kw)
+        t0 = time.perf_counter()
+        r = eng.sparse_elbo_grad(*hargs, **kw)
+        dt = time.perf_counter() - t0
+        out["e2e"] = {"items_per_s": round(ne / dt, 2), "items": ne, "h2d_bytes": int(ne * N * M * 8), "d2h_bytes": int(ne * N * M * 8),
+                      "GBps_each_way": round(ne * N * M * 8 / dt / 1e9, 1), "elbo0": float(r["elbo"][0]),
+                      "api": "bgp_sparse_elbo_grad_host (ctypes, pinned host buffers)"}
     if verbose:
         print(json.dumps(out))
     out["phases_ms"] = phases
