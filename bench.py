@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": reasons}
 
 
-def fp64_peak(device_index=0, torch=None):
+def fp64_peak(device_index=0, torch=None, skip=False):
     """FP64 roofline denominator.  MEASURED_PEAKS.json (driver-written) carries only HBM and bf16, so the fp64 figures are
     measured HERE, in this run, before the timed region: tools/microbench/fp64_peak (compiled by __graft_entry__.build():
     DFMA and DMMA m8n8k4 issue rates over all SMs) and a cuBLAS DGEMM 4096^3 through torch.matmul, with the SM clock sampled
@@ -98,7 +98,7 @@ def fp64_peak(device_index=0, torch=None):
     except Exception:
         pass
     exe = os.path.join(ROOT, "tools", "microbench", "fp64_peak")
-    if not os.path.exists(exe):
+    if skip or not os.path.exists(exe):
         return out
     try:
         sampler = ClockSampler(device_index)
@@ -339,7 +339,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     N, ips = args.cells, args.items
     # fp64 peak of this GPU, measured before anything else is resident (rank-local; the line reports rank 0's)
-    peak_info = fp64_peak(local, torch)
+    peak_info = fp64_peak(local, None if args.no_peak else torch, skip=args.no_peak)
     if world > 1:
         dist.barrier()
     eng = _lib.Engine(local)
@@ -683,6 +683,7 @@ def main():
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-sparse", action="store_true", help="skip the C3 / C4 / FitModel side measurements")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5-shaped (N = 2000) side line")
+    ap.add_argument("--no-peak", action="store_true", help="skip the fp64 peak micro-benchmark (profiler runs)")
     ap.add_argument("--fit-items", type=int, default=148)
     ap.add_argument("--fit-maxiter", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")

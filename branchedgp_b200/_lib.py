@@ -60,6 +60,10 @@ SIGNATURES = {
                                                ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
+    "bgp_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "bgp_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "bgp_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "bgp_gather_results": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "bgp_gaussian_samples_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
@@ -313,6 +317,27 @@ class Engine:
         return mean, var
 
     # ------------------------------------------------------------------ batched fitting (device-resident L-BFGS)
+    # ------------------------------------------------------------------ NCCL gather inside the C ABI
+    def comm_unique_id(self):
+        buf = ctypes.create_string_buffer(128)
+        self._check(self._lib.bgp_comm_unique_id(self._h, buf), "bgp_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.bgp_comm_init(self._h, int(nranks), int(rank), buf), "bgp_comm_init")
+        self._comm_ranks = int(nranks)
+
+    def gather_results(self, local, rows_max):
+        """all_gather of this rank's [rows, k] float64 block -> [nranks, rows_max, k] (zero padded), over the library's own NCCL
+        communicator (bgp_gather_results)."""
+        local = _f64(local)
+        rows, k = local.shape
+        out = np.empty((self._comm_ranks, int(rows_max), k))
+        self._check(self._lib.bgp_gather_results(self._h, _ptr(local) if rows else None, rows, k, int(rows_max), _ptr(out)),
+                    "bgp_gather_results")
+        return out
+
     def gaussian_samples(self, z, mean=None, cov=None, X=None, bv=None, ell=1.0, kvar=1.0, kernel=KERNEL_SQEXP, noise=1e-6,
                          jitter=1e-6):
         """samples[S, n, batch] = mean + chol(cov_d + jitter I) z[d]  for every output d (bgp_gaussian_samples_host).

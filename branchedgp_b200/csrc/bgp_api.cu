@@ -97,6 +97,8 @@ int bgp_destroy(bgp_handle* h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaStream_t s_ : h->lane_streams) cudaStreamDestroy(s_);
     if (h->shared_ready) cudaEventDestroy(h->shared_ready);
+    bgp_comm_destroy(h);
+    if (h->comm_buf) cudaFree(h->comm_buf);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pred_buf) cudaFree(h->pred_buf);
     if (h->ws) cudaFree(h->ws);
@@ -192,8 +194,12 @@ int dense_run(bgp_handle* h, int count, int N, int D, const double* t, const dou
     F.grad_logPhi = grad_logPhi;
 
     auto pm = [&](int phase) { if (mark) prof_mark(h, phase, st); else if (phase >= 0) h->launches++; };
-    for (int item0 = 0; item0 < count; item0 += slots) {
-        const int n = (count - item0 < slots) ? (count - item0) : slots;
+    for (int item0 = 0, n = 0; item0 < count; item0 += n) {
+        n = (count - item0 < slots) ? (count - item0) : slots;
+        // between half and three quarters of an SM count of items: two many-CTA waves of half the items beat one one-CTA wave
+        // (N = 1000: 74 items take 262 ms with two CTAs each, 402 ms with one)
+        // (not inside a fit: there slot == item for the whole call, the slots keep the factorisations of their items)
+        if (wide_mode < 0 && allow_wide && !h->in_fit && 2 * n > h->sm_count && 4 * n <= 3 * h->sm_count) n = (n + 1) / 2;
         P.item0 = item0;
         F.item0 = item0;
         const int last = h->stop_phase > 0 ? h->stop_phase : 99;
@@ -723,15 +729,21 @@ int bgp_sparse_predict_host(bgp_handle* h, int N, int Dtot, int Mz, const double
 int bgp_get_phi_host(bgp_handle* h, int count, int N, const double* logPhi, double* phi) {
     if (!h || count <= 0 || N <= 0 || !logPhi || !phi) return BGP_ERR_ARG;
     CU(cudaSetDevice(h->device));
-    const size_t per_item = (size_t)N * 3 * N * 8;
-    int rc = ensure_stage(h, align_up(per_item, 256) + (size_t)N * 3 * 8);
+    const size_t per_item = (size_t)N * 3 * N * 8, per_out = (size_t)N * 3 * 8;
+    // as many items per trip as a 2 GB staging budget holds (one H2D, one gather launch over all of them, one D2H)
+    size_t chunk = ((size_t)2 << 30) / per_item;
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)count) chunk = (size_t)count;
+    const size_t o_out = align_up(chunk * per_item, 256);
+    int rc = ensure_stage(h, o_out + chunk * per_out);
     if (rc != BGP_OK) return rc;
     char* s = (char*)h->stage;
-    for (int i = 0; i < count; ++i) {
-        CU(cudaMemcpyAsync(s, logPhi + (size_t)i * N * 3 * N, per_item, cudaMemcpyHostToDevice, 0));
-        phi_launch_gather((double*)s, (double*)(s + align_up(per_item, 256)), 1, N, 0);
+    for (size_t i0 = 0; i0 < (size_t)count; i0 += chunk) {
+        const size_t n = ((size_t)count - i0 < chunk) ? ((size_t)count - i0) : chunk;
+        CU(cudaMemcpyAsync(s, logPhi + i0 * (size_t)N * 3 * N, n * per_item, cudaMemcpyHostToDevice, 0));
+        phi_launch_gather((double*)s, (double*)(s + o_out), (int)n, N, 0);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(phi + (size_t)i * N * 3, s + align_up(per_item, 256), (size_t)N * 3 * 8, cudaMemcpyDeviceToHost, 0));
+        CU(cudaMemcpyAsync(phi + i0 * (size_t)N * 3, s + o_out, n * per_out, cudaMemcpyDeviceToHost, 0));
         CU(cudaStreamSynchronize(0));
     }
     return BGP_OK;

@@ -26,10 +26,10 @@
 namespace bgp {
 
 // ------------------------------------------------------------------------------------------------ control area
-// Per slot and per phase: [0] queue head, then cnt[tiles], fin[tiles], col[nM], fail[nM]   (ints, zeroed before every evaluation)
+// Per slot and per phase: [0] queue head, then cnt[tiles], fin[tiles], col[nM], fail[nM], aux[tiles]   (ints, zeroed before every evaluation)
 enum { WPH_CHOLK = 0, WPH_SYRK, WPH_CHOLP, WPH_SOLVE, WPH_TRTRI, WPH_LAUUM, WPH_TRMM, WPH_POST, WPH_ADJ, WPH_COUNT };
 
-__host__ __device__ inline int wide_phase_ints(int nM) { return (8 + nM * (nM + 1) + 2 * nM + 3) & ~3; }
+__host__ __device__ inline int wide_phase_ints(int nM) { return (8 + 3 * (nM * (nM + 1) / 2) + 2 * nM + 3) & ~3; }
 long long dense_wide_ctrl_ints(int nM) { return (long long)WPH_COUNT * wide_phase_ints(nM); }
 
 struct WideCtl {
@@ -38,12 +38,13 @@ struct WideCtl {
     int* fin;
     int* col;
     int* fail;
+    int* aux;
 };
 __device__ __forceinline__ WideCtl wide_ctl(const DenseParams& P, int slot, int phase) {
     const int nM = P.d.nM, nt = nM * (nM + 1) / 2;
     int* base = P.ctrl + (size_t)slot * P.ctrl_stride + (size_t)phase * wide_phase_ints(nM);
     WideCtl C;
-    C.head = base; C.cnt = base + 8; C.fin = C.cnt + nt; C.col = C.fin + nt; C.fail = C.col + nM;
+    C.head = base; C.cnt = base + 8; C.fin = C.cnt + nt; C.col = C.fin + nt; C.fail = C.col + nM; C.aux = C.fail + nM;
     return C;
 }
 __device__ __forceinline__ int tix(int I, int J) { return I * (I + 1) / 2 + J; }
@@ -707,14 +708,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
     auto Pscr = [&](int I) { return PB + (size_t)(I - 1) * 16 * TILE_ELEMS; };
     auto Qscr = [&](int I) { return PB + (size_t)(nM - 1 + I - 1) * 16 * TILE_ELEMS; };
     int ntasks = 1;
-    for (int K = nM - 1; K >= 1; --K) ntasks += (nM - K) + 1 + (K >= 2 ? 1 + (K - 1) * (nM - K) : 0);
+    // BROW(K, J) is one long product (up to nT - 4K k-steps on ONE CTA) that the chain needs two columns later; in the last third of
+    // the sweep it is longer than two columns take.  Long ones are cut into <= 4 chunks of the k range that run as separate
+    // tasks (partial blocks in PB behind the P / Q blocks, two generations) and are added, in chunk order, by the BROW task itself.
+    constexpr int BROW_CH = 24, BROW_NC = 4;
+    const bool chunk_ok = dm.mat_elems / TILE_ELEMS >= (long long)32 * (nM - 1) + (long long)2 * BROW_NC * 16 * (nM - 2) && nM >= 3;
+    auto nchunks = [&](int K_) {
+        int nc = (nT - TPM * K_ + BROW_CH - 1) / BROW_CH;
+        if (nc > BROW_NC) nc = BROW_NC;
+        return (chunk_ok && nc > 1) ? nc : 1;
+    };
+    auto Bscr = [&](int K_, int J_, int c_) {
+        return PB + ((size_t)32 * (nM - 1) + (size_t)((((K_ & 1) * (nM - 2) + J_) * BROW_NC + c_) * 16)) * TILE_ELEMS;
+    };
+    for (int K = nM - 1; K >= 1; --K) {
+        const int ncK = nchunks(K);
+        ntasks += (nM - K) + 1 + (K >= 2 ? 1 + (K - 1) * (ncK > 1 ? ncK + 1 : 1) + (K - 1) * (nM - 1 - K) : 0);
+    }
     int* hpcnt = C.head + 1;   // hyper-gradient partials written so far
     int* qsflag = C.fail;      // qsflag[J]: the Q partials of column J have been summed into the Q block of row J
     Acc acc;
     for (;;) {
         const int t = wq_next(C.head, &s_task);
         if (t >= ntasks) break;
-        int type = 0, I = 0, J = 0, K = 0;   // 0 ADIAG(J), 1 APANEL(I,J), 2 BROW(I=K,J), 3 SC(I,J;K), 4 QSUM(J)
+        int type = 0, I = 0, J = 0, K = 0, ch = 0;   // 0 ADIAG(J), 1 APANEL(I,J), 2 BROW(I=K,J), 3 SC(I,J;K), 4 QSUM(J), 5 BROW chunk (I=K,J,ch)
         if (t == 0) { type = 0; J = nM - 1; }
         else {
             int u = t - 1;
@@ -729,6 +746,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
                     u -= 1;
                 }
                 const int nb = K >= 2 ? K - 1 : 0;
+                const int ncK = nchunks(K);
+                if (ncK > 1) {
+                    if (u < nb * ncK) { type = 5; I = K; J = K - 2 - u / ncK; ch = u % ncK; break; }
+                    u -= nb * ncK;
+                }
                 if (u < nb) { type = 2; I = K; J = K - 2 - u; break; }
                 u -= nb;
                 const int nc = nb * (nM - 1 - K);
@@ -982,23 +1004,62 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
 #pragma unroll
             for (int r = 0; r < PERQ; ++r) dstq[tid + GEMM_THREADS * r] = q[r];
             task_signal(&qsflag[J], 1);
-        } else if (type == 2) {
-            WT_DECL();
-            WT_COUNT(38);
-            // ---- BROW(K, J): tile (K,J) -= Atilde_sym[K, K:] Lc[K:, J]   (one long product over the rows >= K of column K)
+        } else if (type == 5) {
+            // ---- chunk `ch` of BROW(K, J): partial product over its share of the k range -> scratch block
+            const int ncK = nchunks(I);
+            const int klen = nT - TPM * I, per = (klen + ncK - 1) / ncK;
+            const int k0 = TPM * I + ch * per, k1 = min(k0 + per, nT);
             if (tid == 0) {
                 spin_ge(&C.fin[tix(I, I)], 1);
                 for (int k = I + 1; k < nM; ++k) spin_ge(&C.fin[tix(k, I)], 1);
+                // the scratch block was last used two rows up (same parity): its BROW task must have consumed it
+                if (I + 2 <= nM - 1 && nchunks(I + 2) > ch) spin_ge(&C.cnt[tix(I + 2, J)], 1);
             }
             deps_ready();
-            WT_LAP(39);
             acc_zero(acc);
-            gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * I, nT, nullptr);
+            gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, k0, k1, nullptr);
+            double* blkp = Bscr(I, J, ch);
             acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
-                double* tp = LB + packed_tile(it, jt) * TILE_ELEMS;
-                const double2 l = tile_load2_cg(tp, i, j);
-                tile_store2(tp, i, j, l.x - v0, l.y - v1);
+                tile_store2(blkp + (size_t)((it - TPM * I) * TPM + (jt - TPM * J)) * TILE_ELEMS, i, j, v0, v1);
             });
+            task_signal_add(&C.aux[tix(I, J)]);
+        } else if (type == 2) {
+            WT_DECL();
+            WT_COUNT(38);
+            // ---- BROW(K, J): tile (K,J) -= Atilde_sym[K, K:] Lc[K:, J]   (one long product over the rows >= K of column K, or the sum
+            // of its chunks when they ran as separate tasks)
+            const int ncK = nchunks(I);
+            if (ncK > 1) {
+                if (tid == 0) spin_ge(&C.aux[tix(I, J)], ncK);
+                __syncthreads();
+                WT_LAP(39);
+                constexpr int PERB = 16 * TILE_ELEMS / (2 * GEMM_THREADS);   // double2 per thread
+#pragma unroll 4
+                for (int r = 0; r < PERB; ++r) {
+                    const int e2 = tid + GEMM_THREADS * r, tl = e2 >> 9, o2 = e2 & 511;
+                    double2* tp = reinterpret_cast<double2*>(LB + packed_tile(TPM * I + (tl >> 2), TPM * J + (tl & 3)) * TILE_ELEMS) + o2;
+                    double2 v = __ldcg(tp);
+                    for (int c2 = 0; c2 < ncK; ++c2) {
+                        const double2 pv = __ldcg(reinterpret_cast<const double2*>(Bscr(I, J, c2)) + e2);
+                        v.x -= pv.x; v.y -= pv.y;
+                    }
+                    *tp = v;
+                }
+            } else {
+                if (tid == 0) {
+                    spin_ge(&C.fin[tix(I, I)], 1);
+                    for (int k = I + 1; k < nM; ++k) spin_ge(&C.fin[tix(k, I)], 1);
+                }
+                deps_ready();
+                WT_LAP(39);
+                acc_zero(acc);
+                gemm_macro(acc, pipe, opAsym, TPM * I, opLcol, TPM * J, TPM * I, nT, nullptr);
+                acc_foreach(acc, I, J, [&](int it, int jt, int i, int j, double v0, double v1) {
+                    double* tp = LB + packed_tile(it, jt) * TILE_ELEMS;
+                    const double2 l = tile_load2_cg(tp, i, j);
+                    tile_store2(tp, i, j, l.x - v0, l.y - v1);
+                });
+            }
             task_signal(&C.cnt[tix(I, J)], 1);
             WT_LAP(40);
         } else {

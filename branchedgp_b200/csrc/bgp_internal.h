@@ -46,6 +46,8 @@ struct bgp_handle {
     const double* pred_X = nullptr; int pred_T = 0; int pred_full = 0; double* pred_mean = nullptr; double* pred_var = nullptr;
     void* pred_buf = nullptr; size_t pred_buf_bytes = 0;   // predict_f: test inputs, outputs and the full-covariance scratch (grow-only)
     double* pred_ext = nullptr; double* pred_neg1 = nullptr;   // parts of pred_buf: tall matrices of the tiled full covariance, Mp x -1.0
+    // optional NCCL communicator of bgp_comm_init / bgp_gather_results (bgp_comm.cu)
+    void* comm = nullptr; int comm_ranks = 0, comm_rank = 0; void* comm_buf = nullptr; size_t comm_buf_bytes = 0;
     double prof_ms[BGP_NPHASES] = {0};
     long long launches = 0;
 };

@@ -161,6 +161,16 @@ int bgp_sparse_fit_host(bgp_handle* h, int count, int N, int D, int Mz, const do
                         double* hyp, double* phi, double* pred_mean, double* pred_var, int* iters, int* nfev, int* status,
                         double* logPhi_out);
 
+/* Result gather over NCCL (NVLink / NVSwitch) for host programs that only have this C library.  Work items are independent, so the
+ * one exchange of a multi-GPU sweep is the collection of the per-item results.  Every rank: bgp_create on its GPU; rank 0:
+ * bgp_comm_unique_id (128 bytes, shipped to the other ranks by the caller); every rank: bgp_comm_init; then
+ * bgp_gather_results(local rows) -> all[nranks][rows_max][k] on every rank (rows beyond a rank's rows_local are zero).
+ * libnccl.so.2 is opened at run time.  HOST pointers.  (branchedgp_b200/sharding.py does the same through torch.distributed.) */
+int bgp_comm_unique_id(bgp_handle* h, void* id128);
+int bgp_comm_init(bgp_handle* h, int nranks, int rank, const void* id128);
+int bgp_comm_destroy(bgp_handle* h);
+int bgp_gather_results(bgp_handle* h, const double* local, int rows_local, int k, int rows_max, double* all);
+
 /* Batched Gaussian sampling: MBGP AssignGP.sample_prior (MBGP/assigngp.py:800-835) and the correlated branch of
  * predict_f_samples (MBGP/assigngp.py:741-798).  For every output d = 0 .. batch-1:
  *     C_d = cov_d + jitter I,   L_d = chol(C_d),   samples[s][i][d] = mean[d][i] + sum_j L_d[i][j] z[d][j][s]

@@ -32,11 +32,21 @@ def main():
                                        lambda lo, hi: pr["logPhi"][lo:hi], device=torch.device("cuda", dev) if own_gpu else None,
                                        want_grad_logphi=True)
     lo, hi = sharding.shard_range(pr["count"], world, rank)
+    # the same gather through the C ABI's own NCCL communicator (bgp_comm_init / bgp_gather_results); needs one GPU per rank
+    capi = np.zeros((0, 6))
+    if own_gpu:
+        ids = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.comm_init(world, rank, ids[0])
+        mine = np.hstack([res["elbo"][lo:hi, None], res["grad_hyp"][lo:hi], res["status"][lo:hi, None].astype(np.float64)])
+        blocks = eng.gather_results(mine, -(-pr["count"] // world))
+        capi = np.vstack([blocks[r, :sharding.shard_range(pr["count"], world, r)[1] - sharding.shard_range(pr["count"], world, r)[0]]
+                          for r in range(world)])
     if rank == 0:
         one = eng.dense_elbo_grad(pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"], check=False)
         np.savez(out_path, elbo=res["elbo"], grad_hyp=res["grad_hyp"], status=res["status"], one_elbo=one["elbo"],
                  one_grad_hyp=one["grad_hyp"], one_status=one["status"], local_grad=res["grad_logPhi"],
-                 one_grad_block=one["grad_logPhi"][lo:hi], backend=np.array(dist.get_backend()), world=world)
+                 one_grad_block=one["grad_logPhi"][lo:hi], backend=np.array(dist.get_backend()), world=world, capi=capi)
     dist.barrier()
     dist.destroy_process_group()
 

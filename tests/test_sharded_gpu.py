@@ -34,3 +34,6 @@ def test_two_rank_sharded_bound_equals_single_gpu_call(tmp_path, N, wide):
     assert np.array_equal(z["elbo"], z["one_elbo"])            # bit for bit
     assert np.array_equal(z["grad_hyp"], z["one_grad_hyp"])
     assert np.array_equal(z["local_grad"], z["one_grad_block"])
+    if str(z["backend"]) == "nccl":   # one GPU per rank: the C ABI's own NCCL gather returned the same table
+        want = np.hstack([z["one_elbo"][:, None], z["one_grad_hyp"], z["one_status"][:, None].astype(np.float64)])
+        assert np.array_equal(z["capi"], want)
