@@ -432,10 +432,21 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     auto slot_bytes_for = [&](int nsplit) { return (size_t)sparse_layout(N, Mp, Mz, D, nsplit, nch).total * 8; };
     int items_cap = h->max_slots > 0 ? h->max_slots : h->sm_count;
     if (items_cap > count) items_cap = count;
-    int nsplit = (2 * h->sm_count + items_cap * SD - 1) / (items_cap * SD);
-    if (nsplit > 16) nsplit = 16;
-    if (nsplit > nslab) nsplit = nslab;
-    if (nsplit < 1) nsplit = 1;
+    // column splits per sub-problem: the slab kernels launch items x SD x nsplit CTAs of equal length, so what matters is how
+    // close that count comes to a whole number of rounds over the SMs (400 sub-problems unsplit = 2.7 rounds, i.e. three
+    // rounds with the last one two thirds empty; split in four = 10.8 rounds).  Rounds per split, plus a small charge per
+    // split for its fixed work (constants, zero-initialised partials, the reduction over splits), is minimised.
+    int nsplit = 1;
+    {
+        const long long subs = (long long)items_cap * SD;
+        double best = 1e300;
+        for (int n = 1; n <= 16 && n <= nslab; ++n) {
+            const long long rounds = (subs * n + h->sm_count - 1) / h->sm_count;
+            const double cost = (double)rounds / n + 0.015 * n * (double)subs / h->sm_count;
+            if (cost < best - 1e-12) { best = cost; nsplit = n; }
+        }
+        if (const char* e = getenv("BGP_SP_NSPLIT")) { const int n = atoi(e); if (n >= 1 && n <= 16 && n <= nslab) nsplit = n; }
+    }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     const size_t avail = (size_t)(0.9 * (double)(free_b + h->ws_bytes));

@@ -32,7 +32,13 @@ constexpr int NSTAGES = 3;
 constexpr int STAGE_ELEMS = 8 * TILE_ELEMS;          // 4 A tiles + 4 B tiles
 constexpr int STAGE_BYTES = STAGE_ELEMS * 8;          // 64 KB
 constexpr int PIPE_BYTES = NSTAGES * STAGE_BYTES;     // 192 KB
-constexpr int DLD = MB + 1;                           // padded leading dimension of the 128x128 smem scratch
+#ifndef BGP_DLD
+#define BGP_DLD (MB + 4)
+#endif
+// leading dimension of the 128x128 shared-memory scratch of the diagonal-block routines: 132 = 4 mod 16 eight-byte banks makes both
+// DMMA fragment patterns ([g][c] and [c][g]) conflict free (tools/microbench/block_kernels_test: chol128 + trinv128 99k cycles at
+// 129, 72k at 132)
+constexpr int DLD = BGP_DLD;
 constexpr int SMEM_RED_DOUBLES = 3 * 512;
 constexpr int SMEM_BYTES = PIPE_BYTES + SMEM_RED_DOUBLES * 8 + 64;   // + reduction scratch + 2*NSTAGES mbarriers
 

@@ -128,43 +128,58 @@ __device__ __forceinline__ void tile_mm_strip(double* C, int ldc, double c0, dou
 // over all sixteen warps.
 static __device__ void chol128(double* Dm, int& fail, int base_index) {
     __shared__ int fail_s;
-    __shared__ double rinv_s[8];
+    __shared__ double rinv_s[2][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
     constexpr int NB8 = MB / 8;
+    // 8x8 diagonal block J in the registers of the calling warp: lane = row (lanes 8..31 carry identity rows); pivots and
+    // multipliers travel by shuffles, one rsqrt per pivot
+    auto factor_diag = [&](int J) {
+        const int j0 = 8 * J;
+        double a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (lane < 8 && k <= lane) ? Dm[(j0 + lane) * DLD + j0 + k] : ((k == lane) ? 1.0 : 0.0);
+        double rinv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double sacc = a[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) sacc = fma(-a[k], __shfl_sync(0xffffffffu, a[k], j), sacc);
+            double d = __shfl_sync(0xffffffffu, sacc, j);
+            if (!(d > 0.0)) {
+                if (lane == 0 && fail_s == 0) fail_s = base_index + j0 + j + 1;
+                d = 1.0;
+            }
+            rinv[j] = rsqrt(d);
+            a[j] = (lane < j) ? 0.0 : ((lane == j) ? d * rinv[j] : sacc * rinv[j]);
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k <= lane) Dm[(j0 + lane) * DLD + j0 + k] = a[k];
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rinv_s[J & 1][k] = rinv[k];
+        }
+    };
+    // one trailing 8x8 tile (rt, ct) of step J: D -= L_rt L_ct^T (two DMMAs)
+    auto update_tile = [&](int J, int rt, int ct) {
+        const int j0 = 8 * J;
+        double* dp = Dm + (8 * rt + g) * DLD + 8 * ct + 2 * c;
+        double d0 = dp[0], d1 = dp[1];
+        const double* ar = Dm + (8 * rt + g) * DLD + j0 + c;
+        const double* br = Dm + (8 * ct + g) * DLD + j0 + c;
+        dmma(d0, d1, -ar[0], br[0]);
+        dmma(d0, d1, -ar[4], br[4]);
+        dp[0] = d0;
+        dp[1] = d1;
+    };
     if (tid == 0) fail_s = 0;
+    __syncthreads();
+    if (warp == 0) factor_diag(0);
     for (int J = 0; J < NB8; ++J) {
         const int j0 = 8 * J;
-        __syncthreads();
-        if (warp == 0) {
-            // 8x8 diagonal block, lane = row (lanes 8..31 carry identity rows)
-            double a[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = (lane < 8 && k <= lane) ? Dm[(j0 + lane) * DLD + j0 + k] : ((k == lane) ? 1.0 : 0.0);
-            double rinv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                double sacc = a[j];
-#pragma unroll
-                for (int k = 0; k < j; ++k) sacc = fma(-a[k], __shfl_sync(0xffffffffu, a[k], j), sacc);
-                double d = __shfl_sync(0xffffffffu, sacc, j);
-                if (!(d > 0.0)) {
-                    if (lane == 0 && fail_s == 0) fail_s = base_index + j0 + j + 1;
-                    d = 1.0;
-                }
-                rinv[j] = rsqrt(d);
-                a[j] = (lane < j) ? 0.0 : ((lane == j) ? d * rinv[j] : sacc * rinv[j]);
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k <= lane) Dm[(j0 + lane) * DLD + j0 + k] = a[k];
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) rinv_s[k] = rinv[k];
-            }
-        }
         __syncthreads();
         // panel row i:  L_i L_JJ^T = A_i  by forward substitution
         {
@@ -178,26 +193,28 @@ static __device__ void chol128(double* Dm, int& fail, int base_index) {
                     double sacc = row[cc];
 #pragma unroll
                     for (int k = 0; k < cc; ++k) sacc = fma(-l[k], Ld[cc * DLD + k], sacc);
-                    l[cc] = sacc * rinv_s[cc];
+                    l[cc] = sacc * rinv_s[J & 1][cc];
                 }
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) row[cc] = l[cc];
             }
         }
         __syncthreads();
-        // trailing 8x8 tiles (rt, ct), J < ct <= rt: D -= L_rt L_ct^T (two DMMAs each), dealt to the warps
+        // trailing 8x8 tiles (rt, ct), J < ct <= rt.  Lookahead: warp 0 updates the next diagonal tile first and factors it at once
+        // (the serial part of the next step) while the other warps work through the rest of the update.
         const int T0 = J + 1, nrem = NB8 - T0;
-        int rr = 0, cr = warp;
-        for (int t8 = warp; t8 < nrem * (nrem + 1) / 2; t8 += GEMM_WARPS, cr += GEMM_WARPS) {
-            while (cr > rr) { cr -= rr + 1; ++rr; }
-            double* dp = Dm + (8 * (T0 + rr) + g) * DLD + 8 * (T0 + cr) + 2 * c;
-            double d0 = dp[0], d1 = dp[1];
-            const double* ar = Dm + (8 * (T0 + rr) + g) * DLD + j0 + c;
-            const double* br = Dm + (8 * (T0 + cr) + g) * DLD + j0 + c;
-            dmma(d0, d1, -ar[0], br[0]);
-            dmma(d0, d1, -ar[4], br[4]);
-            dp[0] = d0;
-            dp[1] = d1;
+        if (nrem > 0) {
+            if (warp == 0) {
+                update_tile(J, T0, T0);
+                __syncwarp();
+                factor_diag(T0);
+            } else {
+                int rr = 0, cr = warp;   // tile index 0 is (T0, T0): taken by warp 0
+                for (int t8 = warp; t8 < nrem * (nrem + 1) / 2; t8 += GEMM_WARPS - 1, cr += GEMM_WARPS - 1) {
+                    while (cr > rr) { cr -= rr + 1; ++rr; }
+                    update_tile(J, T0 + rr, T0 + cr);
+                }
+            }
         }
     }
     __syncthreads();
@@ -205,44 +222,93 @@ static __device__ void chol128(double* Dm, int& fail, int base_index) {
     __syncthreads();
 }
 
-// In-place inverse of the lower-triangular Dm; the tiles above the diagonal are used as parking space.  With X_pp the inverted
-// diagonal tiles, the off-diagonal tiles follow by distance d = i - p from the diagonal:
-//     X_ip = -X_ii (L_ip X_pp + sum_{p < k < i} L_ik X_kp)
-// All of them are parked in the mirrored upper tiles (p, i), so the original L tiles stay readable until the final move.
+// In-place inverse of the lower-triangular Dm (row-major, leading dimension DLD) by recursive doubling on the fp64 tensor pipe.
+// Level 0: the sixteen 8x8 diagonal blocks, one warp each, in registers (lane = column of the inverse, forward substitution
+// through shuffles).  Level s = 8, 16, 32, 64: every pair of adjacent inverted s x s diagonal blocks A (top) and B (bottom) with
+// the original off-diagonal block C between them becomes the inverse of the 2s x 2s block:  C <- -B (C A).  T = C A is parked
+// in the mirror block above the diagonal (the upper triangle of Dm is scratch), so no second buffer is needed; both products
+// run as 8x8 DMMA tiles dealt to the sixteen warps, with the k ranges cut to the triangles of A and B.  Two CTA barriers per
+// level.  (The version this replaces -- 32x32 diagonal tiles inverted by forward substitution through shared memory, then
+// three levels of tile products on the CUDA cores -- took 23 us per block on the chain of the tile Cholesky.)
 static __device__ void trinv128(double* Dm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, grp = warp >> 2;
-    double* Winv = Dm + MB * DLD;               // 4 inverse diagonal tiles
-    double* Sscr = Winv + TPM * TSCR;           // product tiles of the current distance
+    const int g = lane >> 2, c = lane & 3;
     __syncthreads();
-    if (warp < TPM) trinv32_warp(Dm + (TS * warp) * DLD + TS * warp, DLD, Winv + warp * TSCR, TLD, lane);
-    __syncthreads();
-    for (int d = 1; d < TPM; ++d) {
-        const int ntile = TPM - d;   // tiles (p + d, p), p = 0 .. ntile-1: one group of four warps each
-        if (grp < ntile) {
-            const int p = grp, i = p + d;
-            double* S = Sscr + p * TSCR;
-            tile_mm_strip<false>(S, TLD, 0.0, 1.0, Dm + (TS * i) * DLD + TS * p, DLD, Winv + p * TSCR, TLD, 8 * q, lane);
-            for (int k = p + 1; k < i; ++k)   // X_kp is parked at (p, k)
-                tile_mm_strip<false>(S, TLD, 1.0, 1.0, Dm + (TS * i) * DLD + TS * k, DLD, Dm + (TS * p) * DLD + TS * k, DLD, 8 * q, lane);
+    {
+        // 8x8 diagonal block `warp`: lanes 0..7 hold the rows of L, then lane = column of X = inv(L)
+        const int j0 = 8 * warp;
+        double a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (lane < 8 && k <= lane) ? Dm[(j0 + lane) * DLD + j0 + k] : ((k == lane) ? 1.0 : 0.0);
+        double dl = 1.0;   // this lane's own diagonal entry, then its reciprocal: one division per lane, all in parallel
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (lane == k) dl = a[k];
+        const double rd = 1.0 / dl;
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sacc = fma(-__shfl_sync(0xffffffffu, a[k], i), x[k], sacc);
+            const double rii = __shfl_sync(0xffffffffu, rd, i);   // outside the select: every lane must take part in the shuffle
+            x[i] = (i >= lane) ? sacc * rii : 0.0;
+        }
+        __syncwarp();
+        if (lane < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i >= lane) Dm[(j0 + i) * DLD + j0 + lane] = x[i];
+        }
+    }
+    for (int sz = 8; sz < MB; sz *= 2) {
+        const int npair = MB / (2 * sz), tps = sz / 8;       // pairs of blocks, 8x8 tiles per block side
+        const int ntile = npair * tps * tps;
+        __syncthreads();
+        // T = C A  -> mirror block (rows of A, columns of B).  T[i][j] = sum_{k >= j} C[i][k] A[k][j]  (A lower triangular)
+        for (int t = warp; t < ntile; t += GEMM_WARPS) {
+            const int pr = t / (tps * tps), r = t % (tps * tps), ti = r / tps, tj = r % tps;
+            const int o = pr * 2 * sz;                           // top-left corner of the pair
+            const double* Cb = Dm + (o + sz) * DLD + o;          // C: rows o+sz.., columns o..
+            const double* Ab = Dm + o * DLD + o;
+            // two accumulator chains over alternating 8-wide k blocks, the four fragments of a block loaded before its MMAs
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            const double* ap = Cb + (8 * ti + g) * DLD + c;
+            const int jc = 8 * tj + g;
+            for (int k0 = 8 * tj; k0 < sz; k0 += 8) {
+                const double a0 = ap[k0], a1 = ap[k0 + 4];
+                const double b0 = (k0 + c >= jc) ? Ab[(k0 + c) * DLD + jc] : 0.0;
+                const double b1 = (k0 + 4 + c >= jc) ? Ab[(k0 + 4 + c) * DLD + jc] : 0.0;
+                dmma(d0, d1, a0, b0);
+                dmma(e0, e1, a1, b1);
+            }
+            d0 += e0; d1 += e1;
+            double* Tb = Dm + o * DLD + o + sz;                  // mirror block: rows o.., columns o+sz..
+            Tb[(8 * ti + g) * DLD + 8 * tj + 2 * c] = d0;
+            Tb[(8 * ti + g) * DLD + 8 * tj + 2 * c + 1] = d1;
         }
         __syncthreads();
-        if (grp < ntile) {
-            const int p = grp, i = p + d;
-            tile_mm_strip<false>(Dm + (TS * p) * DLD + TS * i, DLD, 0.0, -1.0, Winv + i * TSCR, TLD, Sscr + p * TSCR, TLD, 8 * q, lane);
+        // C <- -B T.  C[i][j] = -sum_{k <= i} B[i][k] T[k][j]  (B lower triangular)
+        for (int t = warp; t < ntile; t += GEMM_WARPS) {
+            const int pr = t / (tps * tps), r = t % (tps * tps), ti = r / tps, tj = r % tps;
+            const int o = pr * 2 * sz;
+            const double* Bb = Dm + (o + sz) * DLD + o + sz;
+            const double* Tb = Dm + o * DLD + o + sz;
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            const int ir = 8 * ti + g;
+            const double* bp = Tb + c * DLD + 8 * tj + g;
+            for (int k0 = 0; k0 < 8 * ti + 8; k0 += 8) {
+                const double a0 = (k0 + c <= ir) ? -Bb[ir * DLD + k0 + c] : 0.0;
+                const double a1 = (k0 + 4 + c <= ir) ? -Bb[ir * DLD + k0 + 4 + c] : 0.0;
+                const double b0 = bp[k0 * DLD], b1 = bp[(k0 + 4) * DLD];
+                dmma(d0, d1, a0, b0);
+                dmma(e0, e1, a1, b1);
+            }
+            d0 += e0; d1 += e1;
+            double* Cw = Dm + (o + sz) * DLD + o;
+            Cw[(8 * ti + g) * DLD + 8 * tj + 2 * c] = d0;
+            Cw[(8 * ti + g) * DLD + 8 * tj + 2 * c + 1] = d1;
         }
-        __syncthreads();
-    }
-    // parked tiles (p, i) -> (i, p), and the diagonal tiles of the inverse (lower part)
-    for (int e = tid; e < 6 * TS * TS; e += GEMM_THREADS) {
-        const int t6 = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
-        const int ii = t6 < 1 ? 1 : (t6 < 3 ? 2 : 3);            // (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
-        const int pp = t6 < 1 ? 0 : (t6 < 3 ? t6 - 1 : t6 - 3);
-        Dm[(TS * ii + r) * DLD + TS * pp + c] = Dm[(TS * pp + r) * DLD + TS * ii + c];
-    }
-    for (int e = tid; e < TPM * TS * TS; e += GEMM_THREADS) {
-        const int pp = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
-        if (c <= r) Dm[(TS * pp + r) * DLD + TS * pp + c] = Winv[pp * TSCR + r * TLD + c];
     }
     __syncthreads();
 }
