@@ -527,7 +527,9 @@ def run_ours(args):
                              "algorithmic logPhi + gradient bytes (16 B per element) over the measured copy bandwidth, its e2e is bound by "
                              "PCIe (2.4 GB per item each way); C4: algebra flops D (4 Mz^2 3N + Mz^3) over the measured DMMA peak",
                      "C3": time_sparse.run("C3 sparse BGP: N=10000, Mz=30", 10000, 1, 30, 8, False, eng=eng, verbose=False, e2e_items=4),
-                     "C4": time_sparse.run("C4 MBGP: N=500, D=100, Mz=180", 500, 100, 180, 4, True, eng=eng, verbose=False, e2e_items=4)}
+                     "C4": time_sparse.run("C4 MBGP: N=500, D=100, Mz=180", 500, 100, 180, 4, True, eng=eng, verbose=False, e2e_items=4),
+                     "C4_single_model": time_sparse.run("C4 MBGP, ONE joint model in flight (the MBGP optimiser's own call pattern): "
+                                                        "N=500, D=100, Mz=180", 500, 100, 180, 1, True, eng=eng, verbose=False)}
             # C1 (BASELINE.json configs[0]): the drop-in FitModel call on one synthetic gene, N = 100, 10-point grid -- wall
             # clock of the whole call through the public API, SciPy driver and device-resident batched optimiser
             sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -153,3 +153,71 @@ def test_direction_hook_is_the_two_loop_recursion():
         for (s, y), al in zip(zip(S[:col], Y[:col]), alphas[::-1]):
             q += (al - (y @ q) / (s @ y)) * s
         np.testing.assert_allclose(d, -q, rtol=1e-10, atol=1e-14)
+
+
+def test_branching_tree_domain_rule_matches_reference_golden():
+    """BinaryBranchingTree.GetFunctionIndexList / GetFunctionDomains of the one-branch-point tree against values produced by the
+    reference's own class (tests/golden/make_golden_tree.py): trunk for x <= b, both branches after it, the same draws from
+    numpy's global generator, NameError outside (lb, ub]."""
+    import os
+    from branchedgp_b200 import BranchingTree as bt
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tree_index_list.npz"))
+    tree = bt.BinaryBranchingTree(0, 1)
+    tree.add(None, 1, 0.4)
+    np.random.seed(3)
+    Xnew, idx, Xtrue = tree.GetFunctionIndexList(G["x"], fReturnXtrue=True)
+    assert np.array_equal(Xnew, G["Xnew"]) and np.array_equal(Xtrue, G["Xtrue"])
+    assert np.array_equal(np.array([i for ix in idx for i in ix]), G["idx_flat"])
+    assert np.array_equal(np.array([len(ix) for ix in idx]), G["idx_len"])
+    assert np.array_equal(tree.GetFunctionDomains(), G["domains"])
+    fm, _ = tree.GetFunctionBranchTensor()
+    assert np.array_equal(np.isnan(fm), np.isnan(G["fm"])) and np.array_equal(fm[~np.isnan(fm)], G["fm"][~np.isnan(G["fm"])])
+    for bad in ([0.0, 0.5], [0.5, 1.2]):
+        with pytest.raises(NameError):
+            tree.GetFunctionIndexList(np.array(bad))
+
+
+def test_scipy_shim_in_place_gradients_and_pinned_parameter_storage():
+    """gpflow_shim.optimizers.Scipy with a model that writes its gradients in place (the path the CUDA models take) reaches the
+    same minimiser as plain SciPy; a Parameter whose storage was moved into caller-provided ("pinned") memory keeps that storage
+    across assign / set_unconstrained."""
+    import scipy.optimize
+    from branchedgp_b200 import gpflow_shim as gpflow
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((30, 30))
+    A = A @ A.T + 30 * np.eye(30)
+    bvec = rng.standard_normal(30)
+
+    class Quad:
+        def __init__(self):
+            self.x = gpflow.Parameter(np.zeros((5, 6)), name="x")
+            self.s = gpflow.Parameter(1.5, transform=gpflow.positive(), name="s")
+            self.calls = 0
+
+        def training_loss(self):
+            raise AssertionError("the shim must call _loss_and_grad")
+
+        def _loss_and_grad(self, variables, out=None):
+            self.calls += 1
+            x = self.x.view().ravel()
+            s = float(self.s.numpy())
+            f = 0.5 * x @ A @ x - bvec @ x + (s - 2.0) ** 2
+            gx = (A @ x - bvec).reshape(5, 6)
+            gs = np.array(2.0 * (s - 2.0)) * self.s.transform.dforward(self.s.unconstrained_variable)
+            res = []
+            for i, p in enumerate(variables):
+                g = gx if p is self.x else gs
+                np.copyto(out[i], g)
+                res.append(out[i])
+            return f, res
+
+    m = Quad()
+    store = np.empty((5, 6))
+    m.x.pin(lambda shape: store)
+    assert m.x.view() is store
+    gpflow.optimizers.Scipy().minimize(m.training_loss, [m.x, m.s], options=dict(maxiter=200))
+    want = np.linalg.solve(A, bvec)
+    assert np.allclose(m.x.numpy().ravel(), want, atol=1e-5) and abs(float(m.s.numpy()) - 2.0) < 1e-5
+    assert m.x.view() is store and m.calls > 3                     # still the caller's storage after the optimiser's updates
+    m.x.assign(np.ones((5, 6)))
+    assert m.x.view() is store and np.all(store == 1.0)

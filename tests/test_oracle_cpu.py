@@ -139,3 +139,26 @@ def test_oracle_fitmodel_reproduces_the_c1_golden_fixture():
     sub = [grid[4], grid[9]]
     r = fit_ref.fit_model(sub, t, Y, labels, M=0, maxiter=MAXITER, fixHyperparameters=True)
     np.testing.assert_allclose(r["loglik"], gold["fixed/loglik"][[4, 9]], rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,nb", [(1, 4), (2, 4), (3, 4), (4, 3), (6, 3), (9, 2)])
+def test_scatter_form_task_bodies_equal_the_gather_forms(n, nb):
+    """oracle/blocked_dense_wide.py restates, task by task and in queue order, what the multi-CTA pipeline (csrc/bgp_dense_wide.cu)
+    does: right-looking tile Cholesky with the fused last update, Gauss-Jordan inverse of the scaled factor, scatter form of the
+    blocked Cholesky adjoint with its P / Q partials and BROW rows.  They must give what the gather forms of the one-CTA pipeline
+    give (which tests above tie to oracle.bgp_numpy)."""
+    from oracle import blocked_dense as bd, blocked_dense_wide as bw
+    rng = np.random.default_rng(n * 10 + nb)
+    Mp = n * nb
+    A = rng.standard_normal((Mp, Mp))
+    A = A @ A.T + Mp * np.eye(Mp)
+    L1, i1 = bd.chol_left_looking(A, nb)
+    L2, i2 = bw.chol_right_looking(A, nb)
+    assert np.abs(L1 - L2).max() <= 1e-13 * np.abs(L1).max()
+    X1 = np.tril(bd.trtri_inplace(L1, i1, nb))
+    X2 = np.tril(bw.trtri_scatter(L1, i1, nb))
+    assert np.abs(X1 - X2).max() <= 1e-13 * max(1.0, np.abs(X1).max())
+    Lbar = np.tril(rng.standard_normal((Mp, Mp)))
+    A1 = bd.chol_adjoint_gather(L1, i1, Lbar, nb)
+    A2 = bw.chol_adjoint_scatter(L1, i1, Lbar, nb)
+    assert np.abs(A1 - A2).max() <= 1e-12 * max(1.0, np.abs(A1).max())
