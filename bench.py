@@ -416,7 +416,8 @@ def run_ours(args):
     total_flops = sum(fl.values()) * ips * args.steps
     traffic = None   # dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (148-item launch)
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
+        summ = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+        with open(summ if os.path.exists(summ) else os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
             cap = json.load(f).get({"adjoint": "k_adj", "lauum": "k_lauum"}.get(dom, dom), {})
         if "dram_bytes_read" in cap and abs(items_per_launch - 148.0) < 1e-9 and N == 1000:
             traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]

@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
             WT_LAP(34);
             // U = Phi(L_JJ^T Leff)
             acc_zero(acc);
-            gemm_macro(acc, pipe, opLcol, TPM * J, opnd_block(S0, ACC_COLK, TPM * J, TPM * J, 0), TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            gemm_macro(acc, pipe, opLcol, TPM * J, opnd_block(S0, ACC_COLK, TPM * J, TPM * J, 1), TPM * J, TPM * J, TPM * J + TPM, nullptr);
             acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 const int a = it - TPM * J, b = jt - TPM * J;
                 const int gi = it * TS + i, gj = jt * TS + j;
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_wadj(DenseParams P) {
             fence_proxy_async();
             // V = inv(L_JJ)^T U
             acc_zero(acc);
-            gemm_macro(acc, pipe, opInvCol, TPM * J, opnd_block(S1, ACC_COLK, TPM * J, TPM * J, 0), TPM * J, TPM * J, TPM * J + TPM, nullptr);
+            gemm_macro(acc, pipe, opInvCol, TPM * J, opnd_block(S1, ACC_COLK, TPM * J, TPM * J, 1), TPM * J, TPM * J, TPM * J + TPM, nullptr);
             acc_foreach(acc, J, J, [&](int it, int jt, int i, int j, double v0, double v1) {
                 const int a = it - TPM * J, b = jt - TPM * J;
                 tile_store2(S0 + (size_t)(a * TPM + b) * TILE_ELEMS, i, j, v0, v1);
