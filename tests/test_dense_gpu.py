@@ -250,3 +250,26 @@ def test_dense_long_rows_streaming_passes(engine, monkeypatch):
     assert np.allclose(a["grad_hyp"], b["grad_hyp"], rtol=1e-9, atol=0)
     gl = a["grad_logPhi"][0]
     assert np.abs(gl.sum(axis=1)).max() <= 1e-9 * np.abs(gl).sum(axis=1).max()
+
+
+def test_automatic_path_selection_and_wave_split(engine, monkeypatch):
+    """Without BGP_DENSE_WIDE the library picks the pipeline from the number of items in flight: many CTAs per item up to half an
+    SM count of items, two such waves between half and three quarters, one CTA per item above.  100 items (between the two
+    thresholds on a 148-SM part) and 5 items must agree with the forced one-CTA pipeline to round-off, and 3 of them with the oracle."""
+    pr = make_problem(14, D=1, n_genes=10, bs=tuple(np.linspace(0.1, 0.9, 10)), seed=21)
+    args = (pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"])
+    assert pr["count"] == 100
+    monkeypatch.setenv("BGP_DENSE_WIDE", "0")
+    ref = engine.dense_elbo_grad(*args)
+    monkeypatch.delenv("BGP_DENSE_WIDE")
+    auto = engine.dense_elbo_grad(*args)
+    sub = engine.dense_elbo_grad(pr["t"], pr["Y"], pr["item_gene"][:5], pr["b"][:5], pr["prior"], pr["hyp"][:5], pr["logPhi"][:5])
+    assert np.all(ref["status"] == 0) and np.all(auto["status"] == 0) and np.all(sub["status"] == 0)
+    assert np.allclose(auto["elbo"], ref["elbo"], rtol=1e-12, atol=0)
+    assert np.allclose(sub["elbo"], ref["elbo"][:5], rtol=1e-12, atol=0)
+    assert relerr(auto["grad_logPhi"], ref["grad_logPhi"]) <= 1e-10
+    assert np.allclose(auto["grad_hyp"], ref["grad_hyp"], rtol=1e-8, atol=1e-9 * np.abs(ref["grad_hyp"]).max())
+    for k in (0, 57, 99):
+        b, h = pr["b"][k], pr["hyp"][k]
+        e, g = bgp_numpy.dense_value_and_grad(pr["logPhi"][k], pr["Y"][pr["item_gene"][k]], pr["X"], _pz(pr, b), b, h[0], h[1], h[2])
+        _check_item(auto, k, e, g, gb=True)
