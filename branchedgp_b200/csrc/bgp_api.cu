@@ -467,6 +467,8 @@ int bgp_sparse_elbo_grad(bgp_handle* h, int count, int N, int Dtot, int Mz, cons
     P.slot_stride = SL.total;
     P.lay = SL;
     P.t = t; P.Z = Z; P.hyp = hyp; P.bv = b; P.Y = Y; P.item_gene = item_gene;
+    P.dbg_skip = 0;
+    if (const char* e = getenv("BGP_SP_SKIP")) P.dbg_skip = atoi(e);
     P.ws = wsd; P.status = status; P.elbo = elbo; P.grad_hyp = want_grad ? grad_hyp : nullptr; P.grad_b = want_grad ? grad_b : nullptr;
 
     PhiParams F;

@@ -418,19 +418,21 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
             vsl_s[d * SP_SL + jj] = (d < D && !empty && j0 + jj < M) ? ws[SLy.v + (size_t)d * Mp + j0 + jj] : 0.0;
         }
         __syncthreads();
+        if (!(P.dbg_skip & 4))
         for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL, j = j0 + jj;
             const int cell = j / 3, f = j - 3 * cell;
             if (empty || j >= M) Ks[m * LDS_ + jj] = 0.0;
             else if (fz_s[m] != f) Ks[m * LDS_ + jj] = kaz_s[m] * kax_s[cell - cell0];
         }
+        if (!(P.dbg_skip & 4))
         for (int e = tid; e < Mz * ncell; e += SP_T) {
             const int m = e / ncell, lc = e - m * ncell;
             const int jj = 3 * (cell0 + lc) + fz_s[m] - j0;
             if (jj >= 0 && jj < SP_SL && j0 + jj < M) Ks[m * LDS_ + jj] = kbase(zt_s[m] - tc_s[lc], ell, kvar, P.kind);
         }
         __syncthreads();
-        slab_mm<1>(Linv, Ks, Vs, Mz, warp, lane);   // V = Linv K(Z, X_slab)
+        if (!(P.dbg_skip & 1)) slab_mm<1>(Linv, Ks, Vs, Mz, warp, lane);   // V = Linv K(Z, X_slab)
         __syncthreads();
         for (int e = tid; e < Mz * SP_SL; e += SP_T) {
             const int m = e / SP_SL, jj = e % SP_SL;
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_fwd(SparseParams P) {
             Ks[m * LDS_ + jj] = Dls[jj] * Vs[m * LDS_ + jj];
         }
         __syncthreads();
-        slab_outer_lower(Ks, Vs, Pp, Mz, first, 1.0, warp, lane);
+        if (!(P.dbg_skip & 2)) slab_outer_lower(Ks, Vs, Pp, Mz, first, 1.0, warp, lane);
         for (int e = tid; e < D * Mz; e += SP_T) {
             const int d = e / Mz, m = e % Mz;
             double s = 0.0;
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
             dkalx_s[lc] = ws[SLy.dkalx + cell0 + lc]; dkabx_s[lc] = ws[SLy.dkabx + cell0 + lc];
         }
         __syncthreads();
-        slab_mm<0>(Pbar, Vs, Us, Mz, warp, lane);   // U = Pbar V
+        if (!(P.dbg_skip & 1)) slab_mm<0>(Pbar, Vs, Us, Mz, warp, lane);   // U = Pbar V
         __syncthreads();
         // column sums over the Mz rows: warp w takes rows w, w + 8, ...; the partials are combined through Gs (free until the
         // next product) when its Mz rows can hold them, else one warp runs over all rows
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
         }
         __syncthreads();
         // Kuf_bar[k][j] = sum_{m >= k} Linv[m][k] Vbar[m][j]
-        slab_mm<2>(LinvT, Us, Gs, Mz, warp, lane);   // LinvT rows are zero left of the diagonal
+        if (!(P.dbg_skip & 1)) slab_mm<2>(LinvT, Us, Gs, Mz, warp, lane);   // LinvT rows are zero left of the diagonal
         __syncthreads();
         // hyper-gradient through K(Z, X): cross-function entries (products), then the same-function entry of every (row, cell) pair
         if (!empty) {
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(SP_T) k_sp_bwd(SparseParams P) {
             }
         }
         // Lbar partial = -tril(Kuf_bar V^T)
-        slab_outer_lower(Gs, Vs, Lp, Mz, first, -1.0, warp, lane);
+        if (!(P.dbg_skip & 2)) slab_outer_lower(Gs, Vs, Lp, Mz, first, -1.0, warp, lane);
         first = false;
     }
     adel = block_sum(adel, red);

@@ -59,6 +59,7 @@ struct SparseParams {
     double* elbo;            // [count]
     double* grad_hyp;        // [count][3]   d/d ell, var, likvar
     double* grad_b;          // [count][SD]
+    int dbg_skip;            // timing experiments only (BGP_SP_SKIP bit mask: 1 slab products, 2 outer products, 4 K generation); results are wrong when set
 };
 
 }  // namespace bgp
