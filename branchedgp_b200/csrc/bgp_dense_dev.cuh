@@ -44,14 +44,8 @@ __device__ __forceinline__ double kgen(const DenseParams& P, const double* __res
 }
 
 // ------------------------------------------------------------------------------------------------ 128x128 helpers in shared memory
-// The 128x128 diagonal macro blocks are factored and inverted in shared memory as 4x4 blocks of 32x32 tiles.  A 32x32 diagonal
-// tile is factored with its rows in the registers of ONE warp (lane = row, pivots and multipliers travel by shuffles) and
-// inverted by forward substitution (lane = column); every 32x32 tile product is split into four 8-row strips, so the sixteen
-// warps work on up to four tile products at a time.  About twenty CTA barriers per block instead of several hundred.
-// Scratch behind Dm (which occupies MB * DLD doubles of the ring): 4 inverse diagonal tiles + 3 product tiles, ld = TS + 1;
-// the six tiles of Dm above the diagonal serve as parking space for the off-diagonal tiles of the inverse.
-constexpr int TLD = TS + 1;
-constexpr int TSCR = TS * TLD;   // doubles per scratch tile
+// The 128x128 diagonal macro blocks are factored (chol128) and inverted (trinv128) in shared memory, row-major with leading dimension
+// DLD; the upper triangle of the block is scratch.  The 32x32 single-warp routines below serve the batched sampler (bgp_sample.cu).
 
 // In-place lower Cholesky of the 32x32 tile T (leading dimension ld) by ONE warp: lane = row, left-looking (column j is formed
 // from the finished columns to its left, so the inner loop only loads; a fully unrolled register version ran out of instruction
@@ -95,28 +89,6 @@ __device__ __forceinline__ void trinv32_warp(const double* L, int ldl, double* X
         X[i * ldx + lane] = (lane <= i) ? (s0 + s1) * rii : 0.0;
     }
     __syncwarp();
-}
-
-// Rows r0 .. r0+7 of  C = c0 * C + alpha * A * op(B)  on 32x32 tiles, ONE warp: lane = column of C.  C may alias A (the strip of A
-// is read completely before the strip of C is written, and other warps own other strips).
-template <bool TB>
-__device__ __forceinline__ void tile_mm_strip(double* C, int ldc, double c0, double alpha, const double* A, int lda, const double* B,
-                                              int ldb, int r0, int lane) {
-    double acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < TS; ++k) {
-        const double b = TB ? B[lane * ldb + k] : B[k * ldb + lane];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fma(A[(r0 + i) * lda + k], b, acc[i]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        double* c = C + (r0 + i) * ldc + lane;
-        *c = (c0 == 0.0) ? alpha * acc[i] : c0 * *c + alpha * acc[i];
-    }
 }
 
 // In-place lower Cholesky of Dm (row-major, leading dimension DLD).  Non-positive pivots are replaced by 1 and reported.
