@@ -273,3 +273,19 @@ def test_automatic_path_selection_and_wave_split(engine, monkeypatch):
         b, h = pr["b"][k], pr["hyp"][k]
         e, g = bgp_numpy.dense_value_and_grad(pr["logPhi"][k], pr["Y"][pr["item_gene"][k]], pr["X"], _pz(pr, b), b, h[0], h[1], h[2])
         _check_item(auto, k, e, g, gb=True)
+
+
+@pytest.mark.parametrize("N,reps", [(300, 30), (1000, 8)])
+def test_repeated_evaluations_are_bit_identical(engine, N, reps):
+    """Determinism / race stress: the same evaluation repeated must return the same bits every time.  On the many-CTA pipeline the
+    tile tasks are taken by whichever CTA is free and hand their results on through release / acquire counters, TMA reads and
+    L2-only loads; a missing dependency or a stale read would show up here as a run-to-run difference."""
+    pr = make_problem(N, D=1, n_genes=1, bs=(0.35, 0.6) if N <= 300 else (0.5,), seed=123)
+    args = (pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"])
+    first = engine.dense_elbo_grad(*args)
+    assert np.all(first["status"] == 0)
+    for _ in range(reps):
+        again = engine.dense_elbo_grad(*args)
+        assert np.array_equal(again["elbo"], first["elbo"])
+        assert np.array_equal(again["grad_hyp"], first["grad_hyp"])
+        assert np.array_equal(again["grad_logPhi"], first["grad_logPhi"])
