@@ -37,9 +37,10 @@ def _check_item(out, k, e, g, gb=False):
             (nm, out["grad_hyp"][k, j], g[nm])
 
 
-@pytest.mark.parametrize("N,D,kind", [(7, 1, 0), (20, 1, 0), (43, 2, 1), (50, 1, 0), (86, 3, 0), (128, 1, 1)])
+@pytest.mark.parametrize("N,D,kind", [(7, 1, 0), (20, 1, 0), (43, 2, 1), (50, 1, 0), (86, 3, 0), (128, 1, 1), (343, 1, 0), (555, 2, 1)])
 def test_dense_matches_oracle(engine, N, D, kind):
-    """Sizes straddle the 128-row macro block (M = 3N = 21 .. 384): padding, one block, several blocks."""
+    """Sizes straddle the 128-row macro block (M = 3N = 21 .. 1665): padding, one block, several blocks, ragged last blocks (M = 1029 in
+    nine blocks, 1665 in fourteen) where the task graphs of the many-CTA pipeline have every kind of task."""
     pr = make_problem(N, D=D, n_genes=2, bs=(0.25, 0.6), seed=N)
     out = engine.dense_elbo_grad(pr["t"], pr["Y"], pr["item_gene"], pr["b"], pr["prior"], pr["hyp"], pr["logPhi"], kernel=kind)
     for k in range(pr["count"]):
